@@ -88,7 +88,7 @@ def gen_for_lib(plant, N, mode, cfg, out_dir, keep=2):
     ls = be.stage_linesearch(B, xu, dz, m8, mi, rho, np.ones(B, np.float32), 1)
     s = slice(0, keep)
     sl = lambda a: np.ascontiguousarray(a[s])  # noqa: E731
-    G.update(st_B=np.int32(keep), st_dt=np.float32(w["dt"]), st_params=json.dumps(p), st_xu=sl(xu), st_xs=sl(w["xs"]), st_ref=sl(w["ref"]), st_fext=sl(fext), st_rho=sl(rho), st_mu=sl(mu))
+    G.update(st_B=np.int32(min(keep, B)), st_dt=np.float32(w["dt"]), st_params=json.dumps(p), st_xu=sl(xu), st_xs=sl(w["xs"]), st_ref=sl(w["ref"]), st_fext=sl(fext), st_rho=sl(rho), st_mu=sl(mu))
     G.update({"st_kkt_" + k: sl(v) for k, v in kk.items()})
     G.update({"st_schur_" + k: sl(v) for k, v in sc.items()})
     G.update(st_pcg_lam_tol=sl(lam_tol), st_pcg_it_tol=sl(it_tol), st_pcg_lam_cap=sl(lam_cap), st_pcg_it_cap=sl(it_cap))
