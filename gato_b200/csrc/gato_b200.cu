@@ -1,0 +1,638 @@
+// Host side of the B200-native BSQP solver: the C ABI declared in include/gato_b200.h.
+// Mirrors the reference's solver object BSQP<T,BatchSize> (gato/bsqp/bsqp.cuh:20-353): same constructor
+// scalars, same persistent state (lambda and rho survive solves, drho is reset after each solve), same
+// statistics — but the whole solve is enqueued on one stream without any host synchronisation inside
+// (the reference blocks on a device->host copy in every SQP iteration, bsqp.cuh:133-137).
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gato_b200.h"
+#include "bsqp_kernels.cuh"
+
+using namespace gato;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define CUDA_TRY(s, expr)                                                                                         \
+        do {                                                                                                      \
+                cudaError_t e__ = (expr);                                                                         \
+                if (e__ != cudaSuccess) {                                                                         \
+                        char buf__[512];                                                                          \
+                        snprintf(buf__, sizeof(buf__), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+                        (s)->err = buf__;                                                                         \
+                        return GATO_ERR_CUDA;                                                                     \
+                }                                                                                                 \
+        } while (0)
+
+struct Dims {
+        int nq, nx, nu, N, traj, vecp, brow;
+        Dims(int nq_, int N_) : nq(nq_), nx(2 * nq_), nu(nq_), N(N_), traj(3 * nq_ * N_ - nq_), vecp((N_ + 2) * 2 * nq_), brow(3 * 4 * nq_ * nq_) {}
+};
+
+template<typename T>
+struct DevArr {
+        T*     p = nullptr;
+        size_t n = 0;
+        cudaError_t alloc(size_t count)
+        {
+                n = count;
+                cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+                if (e != cudaSuccess) return e;
+                return cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T));
+        }
+        void release()
+        {
+                if (p) cudaFree(p);
+                p = nullptr;
+        }
+};
+
+}  // namespace
+
+struct gato_solver {
+        int          plant, N, B, device;
+        Dims         d;
+        gato_params  prm;
+        bool         adapt_rho = true;
+        cudaStream_t stream = nullptr;
+        bool         own_stream = false;
+        cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+        std::string  err;
+        long         launches = 0;
+        int          max_it;
+        // device state
+        DevArr<float>    Q, R, q, r, A, Bm, c, Qinv, Rinv, S, Pinv, gamma, lambda, dz;
+        DevArr<float>    rho, drho, mu, pcg_tol, fext, merit, merit_cur, merit0, step, ls_merit_log, ls_step_log;
+        DevArr<int>      conv, pcg_log;
+        DevArr<unsigned> num_solved;
+        DevArr<float>    st_xu, st_xs, st_ref, st_xkp1, st_xk, st_uk;  // staging for *_host calls
+        // host mirrors
+        std::vector<float> h_rho_init, h_drho_init;
+        // pinned result buffers
+        int *     h_pcg_log = nullptr, *h_conv = nullptr;
+        unsigned* h_num_solved = nullptr;
+        float *   h_ls_merit = nullptr, *h_ls_step = nullptr, *h_final = nullptr, *h_initial = nullptr;
+        std::vector<int32_t> h_sqp_iters;
+        std::chrono::high_resolution_clock::time_point t_start;
+        bool                                           pending = false;
+        size_t                                         smem_pcg = 0, smem_schur = 0;
+
+        gato_solver(int plant_, int N_, int B_, int dev) : plant(plant_), N(N_), B(B_), device(dev), d(plant_ ? 7 : 6, N_), prm{}, max_it(1) {}
+};
+
+namespace {
+
+template<class P>
+size_t pcg_smem_bytes(int N, int threads)
+{
+        constexpr int NX = 2 * P::NQ, W = 3 * NX, WP = (W + 3) / 4 * 4;
+        const size_t  nrows = (size_t)N * NX, n = (size_t)(N + 2) * NX;
+        return sizeof(float) * (2 * nrows * WP + 5 * n + 40 + 64 * (threads / 32) + (size_t)(N - 1) * NX * NX);
+}
+template<class P>
+size_t schur_smem_bytes(int warps)
+{
+        return sizeof(SchurSmem<2 * P::NQ, P::NQ>) * warps;
+}
+constexpr int kPcgThreads = 512, kSchurWarps = 4;
+
+template<class P>
+int configure_kernels(gato_solver* s)
+{
+        s->smem_pcg = pcg_smem_bytes<P>(s->N, kPcgThreads);
+        s->smem_schur = schur_smem_bytes<P>(kSchurWarps);
+        int maxsm = 0;
+        CUDA_TRY(s, cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+        if (s->smem_pcg > (size_t)maxsm) {
+                s->err = "knot_points too large for the shared-memory-resident PCG kernel on this device";
+                return GATO_ERR_UNSUPPORTED;
+        }
+        CUDA_TRY(s, cudaFuncSetAttribute(k_pcg<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_pcg));
+        CUDA_TRY(s, cudaFuncSetAttribute(k_schur<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_schur));
+        return GATO_OK;
+}
+
+Ctx make_ctx(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref, float dt)
+{
+        Ctx c{};
+        c.N = s->N, c.B = s->B, c.it = 0, c.max_pcg = (int)s->prm.max_pcg_iters, c.adapt = s->adapt_rho ? 1 : 0, c.flags = 0;
+        c.dt = dt;
+        c.thresh = (float)(uint32_t)s->B * s->prm.solve_ratio;
+        c.cs = Costs{s->prm.q_cost, s->prm.qd_cost, s->prm.u_cost, s->prm.N_cost, s->prm.q_lim_cost, s->prm.vel_lim_cost, s->prm.ctrl_lim_cost};
+        c.xu = d_xu, c.xs = d_xs, c.ref = d_ref, c.fext = s->fext.p;
+        c.Q = s->Q.p, c.R = s->R.p, c.q = s->q.p, c.r = s->r.p, c.A = s->A.p, c.Bm = s->Bm.p, c.c = s->c.p, c.Qinv = s->Qinv.p, c.Rinv = s->Rinv.p;
+        c.S = s->S.p, c.Pinv = s->Pinv.p, c.gamma = s->gamma.p, c.lambda = s->lambda.p, c.dz = s->dz.p;
+        c.rho = s->rho.p, c.drho = s->drho.p, c.merit = s->merit.p, c.merit_cur = s->merit_cur.p, c.step = s->step.p;
+        c.mu = s->mu.p, c.pcg_tol = s->pcg_tol.p;
+        c.conv = s->conv.p, c.num_solved = s->num_solved.p, c.pcg_log = s->pcg_log.p, c.ls_merit_log = s->ls_merit_log.p, c.ls_step_log = s->ls_step_log.p;
+        return c;
+}
+
+inline int merit_threads(int na, int N)
+{
+        const int cap = na == 1 ? 128 : 256;
+        int       t = na * N;
+        t = (t + 31) / 32 * 32;
+        return t > cap ? cap : t;
+}
+
+template<class P>
+void launch_kkt(gato_solver* s, const Ctx& c)
+{
+        const int items = c.B * c.N;
+        k_kkt<P><<<(items + 31) / 32, 32, 0, s->stream>>>(c);
+        s->launches++;
+}
+template<class P>
+void launch_schur(gato_solver* s, const Ctx& c)
+{
+        const int items = c.B * c.N;
+        k_schur<P><<<(items + kSchurWarps - 1) / kSchurWarps, kSchurWarps * 32, s->smem_schur, s->stream>>>(c);
+        s->launches++;
+}
+template<class P>
+void launch_pcg(gato_solver* s, const Ctx& c)
+{
+        k_pcg<P><<<c.B, kPcgThreads, s->smem_pcg, s->stream>>>(c);
+        s->launches++;
+}
+template<class P, int NA>
+void launch_merit(gato_solver* s, const Ctx& c)
+{
+        k_merit_ls<P, NA><<<c.B, merit_threads(NA, c.N), sizeof(float) * (NA * c.N + NA), s->stream>>>(c);
+        s->launches++;
+}
+
+// BSQP::solve (bsqp.cuh:103-197) as one stream of launches
+template<class P>
+int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref, float dt)
+{
+        const int B = s->B;
+        Ctx       c = make_ctx(s, d_xu, d_xs, d_ref, dt);
+        CUDA_TRY(s, cudaMemsetAsync(s->conv.p, 0, sizeof(int) * B, s->stream));
+        CUDA_TRY(s, cudaMemsetAsync(s->num_solved.p, 0, sizeof(unsigned) * s->max_it, s->stream));
+        CUDA_TRY(s, cudaMemsetAsync(s->pcg_log.p, 0, sizeof(int) * (size_t)s->max_it * B, s->stream));
+        // initial merit (dz = 0, alpha = 1)  bsqp.cuh:116-118
+        c.flags = F_MERIT;
+        launch_merit<P, 1>(s, c);
+        CUDA_TRY(s, cudaMemcpyAsync(s->merit0.p, s->merit_cur.p, sizeof(float) * B, cudaMemcpyDeviceToDevice, s->stream));
+        for (int it = 0; it < s->max_it; it++) {
+                c.it = it;
+                c.flags = F_CHECK_STOP;
+                launch_kkt<P>(s, c);
+                launch_schur<P>(s, c);
+                c.flags = F_CHECK_STOP | F_K2 | F_PCG | F_DZ | F_BOOK;
+                launch_pcg<P>(s, c);
+                c.flags = F_CHECK_STOP | F_MERIT | F_LS;
+                launch_merit<P, kNumAlphas>(s, c);
+        }
+        // final merit on the updated trajectory  bsqp.cuh:180-182
+        c.flags = F_MERIT;
+        launch_merit<P, 1>(s, c);
+        CUDA_TRY(s, cudaGetLastError());
+        // results -> pinned host buffers
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_num_solved, s->num_solved.p, sizeof(unsigned) * s->max_it, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_pcg_log, s->pcg_log.p, sizeof(int) * (size_t)s->max_it * B, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_ls_merit, s->ls_merit_log.p, sizeof(float) * (size_t)s->max_it * B, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_ls_step, s->ls_step_log.p, sizeof(float) * (size_t)s->max_it * B, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_conv, s->conv.p, sizeof(int) * B, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_final, s->merit_cur.p, sizeof(float) * B, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_initial, s->merit0.p, sizeof(float) * B, cudaMemcpyDeviceToHost, s->stream));
+        // drho is reset after every solve (bsqp.cuh:189); lambda and rho persist
+        CUDA_TRY(s, cudaMemcpyAsync(s->drho.p, s->h_drho_init.data(), sizeof(float) * B, cudaMemcpyHostToDevice, s->stream));
+        return GATO_OK;
+}
+
+int dispatch_enqueue(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref, float dt)
+{
+        return s->plant == GATO_PLANT_IIWA14 ? enqueue_solve<Iiwa14>(s, d_xu, d_xs, d_ref, dt) : enqueue_solve<Indy7>(s, d_xu, d_xs, d_ref, dt);
+}
+
+int fill_stats(gato_solver* s, gato_stats* st)
+{
+        const int B = s->B;
+        // outer iterations executed: up to and including the first one whose count met the early-exit test (bsqp.cuh:165)
+        const float thresh = (float)(uint32_t)B * s->prm.solve_ratio;
+        int         n_pcg = s->max_it, n_ls = s->max_it;
+        for (int i = 0; i < s->max_it; i++)
+                if ((float)s->h_num_solved[i] >= thresh) {
+                        n_pcg = i + 1;
+                        n_ls = i;
+                        break;
+                }
+        for (int b = 0; b < B; b++) s->h_sqp_iters[b] = n_pcg;  // every solve is counted once per outer iteration (bsqp.cuh:153-162)
+        if (st) {
+                st->batch = B;
+                st->n_pcg = n_pcg, st->n_ls = n_ls;
+                st->sqp_iters = s->h_sqp_iters.data();
+                st->kkt_converged = s->h_conv;
+                st->pcg_iters = s->h_pcg_log;
+                st->ls_min_merit = s->h_ls_merit;
+                st->ls_step_size = s->h_ls_step;
+                st->final_merit = s->h_final;
+                st->initial_merit = s->h_initial;
+        }
+        return GATO_OK;
+}
+
+int check_dev(gato_solver* s)
+{
+        CUDA_TRY(s, cudaSetDevice(s->device));
+        return GATO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gato_dims(int plant, int N, int* nx, int* nu, int* traj)
+{
+        if ((plant != 0 && plant != 1) || N < 3) return GATO_ERR_ARG;
+        Dims d(plant ? 7 : 6, N);
+        if (nx) *nx = d.nx;
+        if (nu) *nu = d.nu;
+        if (traj) *traj = d.traj;
+        return GATO_OK;
+}
+
+const char* gato_last_error(const gato_solver* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+long        gato_kernel_launches(const gato_solver* s) { return s ? s->launches : 0; }
+
+int gato_create(gato_solver** out, int plant, int N, int B, int device, void* stream, const gato_params* prm)
+{
+        if (!out || !prm || (plant != 0 && plant != 1) || N < 3 || B < 1) {
+                g_create_error = "invalid argument";
+                return GATO_ERR_ARG;
+        }
+        gato_solver* s = new gato_solver(plant, N, B, device);
+        s->prm = *prm;
+        s->max_it = (int)std::max<uint32_t>(prm->max_sqp_iters, 1u);
+        auto fail = [&](int rc) {
+                g_create_error = s->err;
+                gato_destroy(s);
+                *out = nullptr;
+                return rc;
+        };
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+                s->err = "no CUDA device available (gato_b200 has no CPU fallback)";
+                return fail(GATO_ERR_CUDA);
+        }
+        if (check_dev(s)) return fail(GATO_ERR_CUDA);
+        if (stream) {
+                s->stream = (cudaStream_t)stream;
+        } else {
+                if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+                        s->err = "cudaStreamCreate failed";
+                        return fail(GATO_ERR_CUDA);
+                }
+                s->own_stream = true;
+        }
+        int rc = plant == GATO_PLANT_IIWA14 ? configure_kernels<Iiwa14>(s) : configure_kernels<Indy7>(s);
+        if (rc) return fail(rc);
+        const Dims&  d = s->d;
+        const size_t b = B, it = s->max_it;
+        cudaError_t  e = cudaSuccess;
+        auto         A = [&](auto& arr, size_t n) {
+                if (e == cudaSuccess) e = arr.alloc(n);
+        };
+        A(s->Q, b * d.nx * d.nx * N), A(s->R, b * d.nu * d.nu * N), A(s->q, b * d.nx * N), A(s->r, b * d.nu * N), A(s->A, b * d.nx * d.nx * N), A(s->Bm, b * d.nx * d.nu * N);
+        A(s->c, b * d.nx * N), A(s->Qinv, b * d.nx * d.nx * N), A(s->Rinv, b * d.nu * d.nu * N);
+        A(s->S, b * d.brow * N), A(s->Pinv, b * d.brow * N), A(s->gamma, b * d.vecp), A(s->lambda, b * d.vecp), A(s->dz, b * d.traj);
+        A(s->rho, b), A(s->drho, b), A(s->mu, b), A(s->pcg_tol, b), A(s->fext, 6 * b), A(s->merit, kNumAlphas * b), A(s->merit_cur, b), A(s->merit0, b), A(s->step, b);
+        A(s->ls_merit_log, it * b), A(s->ls_step_log, it * b), A(s->conv, b), A(s->pcg_log, it * b), A(s->num_solved, it);
+        A(s->st_xu, b * d.traj), A(s->st_xs, b * d.nx), A(s->st_ref, b * 6 * N), A(s->st_xkp1, b * d.nx), A(s->st_xk, d.nx), A(s->st_uk, d.nu);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_pcg_log, sizeof(int) * it * b);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_conv, sizeof(int) * b);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_num_solved, sizeof(unsigned) * it);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_ls_merit, sizeof(float) * it * b);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_ls_step, sizeof(float) * it * b);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_final, sizeof(float) * b);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_initial, sizeof(float) * b);
+        if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+        if (e != cudaSuccess) {
+                s->err = std::string("allocation failed: ") + cudaGetErrorString(e);
+                return fail(GATO_ERR_CUDA);
+        }
+        s->h_sqp_iters.assign(B, 0);
+        // per-batch hyper-parameters  (bsqp.cuh:48-58)
+        s->h_rho_init.assign(B, prm->rho);
+        s->h_drho_init.assign(B, 1.0f);
+        std::vector<float> mu(B, prm->mu), tol(B, prm->pcg_tol);
+        cudaMemcpy(s->rho.p, s->h_rho_init.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
+        cudaMemcpy(s->drho.p, s->h_drho_init.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
+        cudaMemcpy(s->mu.p, mu.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
+        cudaMemcpy(s->pcg_tol.p, tol.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
+        if (cudaDeviceSynchronize() != cudaSuccess) {
+                s->err = "initialisation failed";
+                return fail(GATO_ERR_CUDA);
+        }
+        *out = s;
+        return GATO_OK;
+}
+
+void gato_destroy(gato_solver* s)
+{
+        if (!s) return;
+        cudaSetDevice(s->device);
+        if (s->stream) cudaStreamSynchronize(s->stream);
+        for (auto* a : {&s->Q, &s->R, &s->q, &s->r, &s->A, &s->Bm, &s->c, &s->Qinv, &s->Rinv, &s->S, &s->Pinv, &s->gamma, &s->lambda, &s->dz, &s->rho, &s->drho, &s->mu, &s->pcg_tol, &s->fext,
+                        &s->merit, &s->merit_cur, &s->merit0, &s->step, &s->ls_merit_log, &s->ls_step_log, &s->st_xu, &s->st_xs, &s->st_ref, &s->st_xkp1, &s->st_xk, &s->st_uk})
+                a->release();
+        s->conv.release(), s->pcg_log.release(), s->num_solved.release();
+        for (void* p : {(void*)s->h_pcg_log, (void*)s->h_conv, (void*)s->h_num_solved, (void*)s->h_ls_merit, (void*)s->h_ls_step, (void*)s->h_final, (void*)s->h_initial})
+                if (p) cudaFreeHost(p);
+        if (s->ev0) cudaEventDestroy(s->ev0);
+        if (s->ev1) cudaEventDestroy(s->ev1);
+        if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+        delete s;
+}
+
+int gato_set_batch(gato_solver* s, int field, const float* h, int set_default)
+{
+        if (!s || !h) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        const size_t B = s->B;
+        float*       dst = nullptr;
+        size_t       n = B;
+        switch (field) {
+                case GATO_F_EXT: dst = s->fext.p, n = 6 * B; break;
+                case GATO_RHO:
+                        dst = s->rho.p;
+                        if (set_default) s->h_rho_init.assign(h, h + B);
+                        break;
+                case GATO_DRHO:
+                        dst = s->drho.p;
+                        if (set_default) s->h_drho_init.assign(h, h + B);
+                        break;
+                case GATO_MU: dst = s->mu.p; break;
+                case GATO_PCG_TOL: dst = s->pcg_tol.p; break;
+                default: s->err = "unknown batch field"; return GATO_ERR_ARG;
+        }
+        CUDA_TRY(s, cudaMemcpyAsync(dst, h, sizeof(float) * n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        return GATO_OK;
+}
+
+int gato_reset(gato_solver* s, int field)
+{
+        if (!s) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        if (field == GATO_RESET_DUAL) {
+                CUDA_TRY(s, cudaMemsetAsync(s->lambda.p, 0, sizeof(float) * s->lambda.n, s->stream));
+        } else if (field == GATO_RESET_RHO) {
+                CUDA_TRY(s, cudaMemcpyAsync(s->rho.p, s->h_rho_init.data(), sizeof(float) * s->B, cudaMemcpyHostToDevice, s->stream));
+                CUDA_TRY(s, cudaMemcpyAsync(s->drho.p, s->h_drho_init.data(), sizeof(float) * s->B, cudaMemcpyHostToDevice, s->stream));
+        } else {
+                s->err = "unknown reset field";
+                return GATO_ERR_ARG;
+        }
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        return GATO_OK;
+}
+
+int gato_set_rho_adaptation(gato_solver* s, int enabled)
+{
+        if (!s) return GATO_ERR_ARG;
+        s->adapt_rho = enabled != 0;
+        return GATO_OK;
+}
+
+int gato_solve_async(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref, float dt)
+{
+        if (!s || !d_xu || !d_xs || !d_ref) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        s->t_start = std::chrono::high_resolution_clock::now();
+        CUDA_TRY(s, cudaEventRecord(s->ev0, s->stream));
+        int rc = dispatch_enqueue(s, d_xu, d_xs, d_ref, dt);
+        if (rc) return rc;
+        CUDA_TRY(s, cudaEventRecord(s->ev1, s->stream));
+        s->pending = true;
+        return GATO_OK;
+}
+
+int gato_solve_wait(gato_solver* s, gato_stats* st)
+{
+        if (!s) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        s->pending = false;
+        fill_stats(s, st);
+        if (st) {
+                st->solve_time_us = std::chrono::duration<double, std::micro>(std::chrono::high_resolution_clock::now() - s->t_start).count();
+                float ms = 0;
+                CUDA_TRY(s, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+                st->device_time_ms = ms;
+        }
+        return GATO_OK;
+}
+
+int gato_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref, float dt, gato_stats* st)
+{
+        int rc = gato_solve_async(s, d_xu, d_xs, d_ref, dt);
+        if (rc) return rc;
+        return gato_solve_wait(s, st);
+}
+
+int gato_solve_host(gato_solver* s, float* h_xu, const float* h_xs, const float* h_ref, float dt, gato_stats* st)
+{
+        if (!s || !h_xu || !h_xs || !h_ref) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        const Dims& d = s->d;
+        const auto  t0 = std::chrono::high_resolution_clock::now();
+        CUDA_TRY(s, cudaMemcpyAsync(s->st_xu.p, h_xu, sizeof(float) * (size_t)s->B * d.traj, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->st_xs.p, h_xs, sizeof(float) * (size_t)s->B * d.nx, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->st_ref.p, h_ref, sizeof(float) * (size_t)s->B * 6 * s->N, cudaMemcpyHostToDevice, s->stream));
+        int rc = gato_solve_async(s, s->st_xu.p, s->st_xs.p, s->st_ref.p, dt);
+        if (rc) return rc;
+        CUDA_TRY(s, cudaMemcpyAsync(h_xu, s->st_xu.p, sizeof(float) * (size_t)s->B * d.traj, cudaMemcpyDeviceToHost, s->stream));
+        rc = gato_solve_wait(s, st);
+        if (st) st->solve_time_us = std::chrono::duration<double, std::micro>(std::chrono::high_resolution_clock::now() - t0).count();
+        return rc;
+}
+
+int gato_get_device_pointers(gato_solver* s, float** d_xu, float** d_xs, float** d_ref)
+{
+        if (!s) return GATO_ERR_ARG;
+        if (d_xu) *d_xu = s->st_xu.p;
+        if (d_xs) *d_xs = s->st_xs.p;
+        if (d_ref) *d_ref = s->st_ref.p;
+        return GATO_OK;
+}
+
+int gato_get_merits(gato_solver* s, float* h_final, float* h_initial)
+{
+        if (!s) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        if (h_final) CUDA_TRY(s, cudaMemcpy(h_final, s->merit_cur.p, sizeof(float) * s->B, cudaMemcpyDeviceToHost));
+        if (h_initial) CUDA_TRY(s, cudaMemcpy(h_initial, s->merit0.p, sizeof(float) * s->B, cudaMemcpyDeviceToHost));
+        return GATO_OK;
+}
+
+int gato_sim_forward(gato_solver* s, float* d_xkp1, const float* d_xk, const float* d_uk, float dt)
+{
+        if (!s || !d_xkp1 || !d_xk || !d_uk) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        const int T = 64, G = (s->B + T - 1) / T;
+        if (s->plant == GATO_PLANT_IIWA14)
+                k_sim_forward<Iiwa14><<<G, T, 0, s->stream>>>(s->B, d_xkp1, d_xk, d_uk, s->fext.p, dt);
+        else
+                k_sim_forward<Indy7><<<G, T, 0, s->stream>>>(s->B, d_xkp1, d_xk, d_uk, s->fext.p, dt);
+        s->launches++;
+        CUDA_TRY(s, cudaGetLastError());
+        return GATO_OK;
+}
+
+int gato_sim_forward_host(gato_solver* s, float* h_xkp1, const float* h_xk, const float* h_uk, float dt)
+{
+        if (!s || !h_xkp1 || !h_xk || !h_uk) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        CUDA_TRY(s, cudaMemcpyAsync(s->st_xk.p, h_xk, sizeof(float) * s->d.nx, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->st_uk.p, h_uk, sizeof(float) * s->d.nu, cudaMemcpyHostToDevice, s->stream));
+        int rc = gato_sim_forward(s, s->st_xkp1.p, s->st_xk.p, s->st_uk.p, dt);
+        if (rc) return rc;
+        CUDA_TRY(s, cudaMemcpyAsync(h_xkp1, s->st_xkp1.p, sizeof(float) * (size_t)s->B * s->d.nx, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        return GATO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage-level entry points: run ONE product kernel (or kernel phase) on host buffers, for parity tests
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct StageSolver {
+        gato_solver* s = nullptr;
+        StageSolver(int plant, int N, int B, const float* cost7, int max_pcg = 0)
+        {
+                gato_params p{};
+                p.dt = 0.01f, p.max_sqp_iters = 1, p.max_pcg_iters = (uint32_t)max_pcg, p.solve_ratio = 1.0f, p.mu = 10.0f, p.rho = 0.0f;
+                if (cost7) p.q_cost = cost7[0], p.qd_cost = cost7[1], p.u_cost = cost7[2], p.N_cost = cost7[3], p.q_lim_cost = cost7[4], p.vel_lim_cost = cost7[5], p.ctrl_lim_cost = cost7[6];
+                gato_create(&s, plant, N, B, 0, nullptr, &p);
+        }
+        ~StageSolver() { gato_destroy(s); }
+        bool up(DevArr<float>& a, const float* h) { return cudaMemcpyAsync(a.p, h, sizeof(float) * a.n, cudaMemcpyHostToDevice, s->stream) == cudaSuccess; }
+        bool down(float* h, DevArr<float>& a) { return cudaMemcpyAsync(h, a.p, sizeof(float) * a.n, cudaMemcpyDeviceToHost, s->stream) == cudaSuccess; }
+        int  finish()
+        {
+                cudaError_t e = cudaStreamSynchronize(s->stream);
+                if (e == cudaSuccess) e = cudaGetLastError();
+                if (e != cudaSuccess) {
+                        fprintf(stderr, "gato stage: %s\n", cudaGetErrorString(e));
+                        return GATO_ERR_CUDA;
+                }
+                return GATO_OK;
+        }
+};
+#define PLANT_CALL(plant, fn, ...) ((plant) == GATO_PLANT_IIWA14 ? fn<Iiwa14>(__VA_ARGS__) : fn<Indy7>(__VA_ARGS__))
+}  // namespace
+
+int gato_stage_kkt(int plant, int N, int B, const float* xu, const float* xs, const float* ref, const float* fext, float dt, const float* cost7, float* Q, float* R, float* q, float* r, float* A,
+                   float* Bm, float* c)
+{
+        StageSolver t(plant, N, B, cost7);
+        if (!t.s) return GATO_ERR_CUDA;
+        gato_solver* s = t.s;
+        t.up(s->st_xu, xu), t.up(s->st_xs, xs), t.up(s->st_ref, ref), t.up(s->fext, fext);
+        Ctx ctx = make_ctx(s, s->st_xu.p, s->st_xs.p, s->st_ref.p, dt);
+        PLANT_CALL(plant, launch_kkt, s, ctx);
+        t.down(Q, s->Q), t.down(R, s->R), t.down(q, s->q), t.down(r, s->r), t.down(A, s->A), t.down(Bm, s->Bm), t.down(c, s->c);
+        return t.finish();
+}
+
+int gato_stage_schur(int plant, int N, int B, float* Q, float* R, const float* q, const float* r, const float* A, const float* Bm, const float* c, const float* rho, float* S, float* Pinv,
+                     float* gamma)
+{
+        StageSolver t(plant, N, B, nullptr);
+        if (!t.s) return GATO_ERR_CUDA;
+        gato_solver* s = t.s;
+        t.up(s->Q, Q), t.up(s->R, R), t.up(s->q, q), t.up(s->r, r), t.up(s->A, A), t.up(s->Bm, Bm), t.up(s->c, c), t.up(s->rho, rho);
+        Ctx ctx = make_ctx(s, s->st_xu.p, s->st_xs.p, s->st_ref.p, 0.01f);
+        PLANT_CALL(plant, launch_schur, s, ctx);
+        ctx.flags = F_K2 | F_WRITE_P;
+        PLANT_CALL(plant, launch_pcg, s, ctx);
+        t.down(S, s->S), t.down(Pinv, s->Pinv), t.down(gamma, s->gamma), t.down(Q, s->Qinv), t.down(R, s->Rinv);
+        return t.finish();
+}
+
+int gato_stage_pcg(int plant, int N, int B, const float* S, const float* Pinv, const float* gamma, float* lambda, const float* eps, int max_iters, const int* kkt_conv, int* iters)
+{
+        StageSolver t(plant, N, B, nullptr, max_iters);
+        if (!t.s) return GATO_ERR_CUDA;
+        gato_solver* s = t.s;
+        t.up(s->S, S), t.up(s->Pinv, Pinv), t.up(s->gamma, gamma), t.up(s->lambda, lambda), t.up(s->pcg_tol, eps);
+        cudaMemcpyAsync(s->conv.p, kkt_conv, sizeof(int) * B, cudaMemcpyHostToDevice, s->stream);
+        Ctx ctx = make_ctx(s, s->st_xu.p, s->st_xs.p, s->st_ref.p, 0.01f);
+        ctx.flags = F_PCG;
+        PLANT_CALL(plant, launch_pcg, s, ctx);
+        t.down(lambda, s->lambda);
+        cudaMemcpyAsync(iters, s->pcg_log.p, sizeof(int) * B, cudaMemcpyDeviceToHost, s->stream);
+        return t.finish();
+}
+
+int gato_stage_dz(int plant, int N, int B, const float* lambda, const float* Qinv, const float* Rinv, float* q, float* r, const float* A, const float* Bm, float* dz)
+{
+        StageSolver t(plant, N, B, nullptr);
+        if (!t.s) return GATO_ERR_CUDA;
+        gato_solver* s = t.s;
+        t.up(s->lambda, lambda), t.up(s->Qinv, Qinv), t.up(s->Rinv, Rinv), t.up(s->q, q), t.up(s->r, r), t.up(s->A, A), t.up(s->Bm, Bm);
+        Ctx ctx = make_ctx(s, s->st_xu.p, s->st_xs.p, s->st_ref.p, 0.01f);
+        ctx.flags = F_DZ;
+        PLANT_CALL(plant, launch_pcg, s, ctx);
+        t.down(dz, s->dz), t.down(q, s->q), t.down(r, s->r);
+        return t.finish();
+}
+
+int gato_stage_merit(int plant, int N, int B, const float* xu, const float* dz, const float* xs, const float* ref, const float* mu, const float* fext, float dt, const float* cost7, int num_alphas,
+                     float* merit)
+{
+        StageSolver t(plant, N, B, cost7);
+        if (!t.s) return GATO_ERR_CUDA;
+        gato_solver* s = t.s;
+        t.up(s->st_xu, xu), t.up(s->dz, dz), t.up(s->st_xs, xs), t.up(s->st_ref, ref), t.up(s->mu, mu), t.up(s->fext, fext);
+        Ctx ctx = make_ctx(s, s->st_xu.p, s->st_xs.p, s->st_ref.p, dt);
+        ctx.flags = F_MERIT;
+        ctx.ls_merit_log = nullptr;
+        if (num_alphas == 1) {
+                if (plant == GATO_PLANT_IIWA14)
+                        launch_merit<Iiwa14, 1>(s, ctx);
+                else
+                        launch_merit<Indy7, 1>(s, ctx);
+                cudaMemcpyAsync(merit, s->merit_cur.p, sizeof(float) * B, cudaMemcpyDeviceToHost, s->stream);
+        } else {
+                if (plant == GATO_PLANT_IIWA14)
+                        launch_merit<Iiwa14, kNumAlphas>(s, ctx);
+                else
+                        launch_merit<Indy7, kNumAlphas>(s, ctx);
+                t.down(merit, s->merit);
+        }
+        return t.finish();
+}
+
+int gato_stage_linesearch(int plant, int N, int B, float* xu, const float* dz, const float* merit8, float* merit_init, float* step, float* rho, float* drho, int adapt)
+{
+        StageSolver t(plant, N, B, nullptr);
+        if (!t.s) return GATO_ERR_CUDA;
+        gato_solver* s = t.s;
+        s->adapt_rho = adapt != 0;
+        t.up(s->st_xu, xu), t.up(s->dz, dz), t.up(s->merit, merit8), t.up(s->merit_cur, merit_init), t.up(s->rho, rho), t.up(s->drho, drho);
+        Ctx ctx = make_ctx(s, s->st_xu.p, s->st_xs.p, s->st_ref.p, 0.01f);
+        ctx.flags = F_LS;
+        ctx.ls_merit_log = nullptr;
+        if (plant == GATO_PLANT_IIWA14)
+                launch_merit<Iiwa14, kNumAlphas>(s, ctx);
+        else
+                launch_merit<Indy7, kNumAlphas>(s, ctx);
+        t.down(xu, s->st_xu), t.down(merit_init, s->merit_cur), t.down(step, s->step), t.down(rho, s->rho), t.down(drho, s->drho);
+        return t.finish();
+}
+
+}  // extern "C"

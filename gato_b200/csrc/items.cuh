@@ -1,0 +1,177 @@
+// Per-work-item stages of the BSQP path built on rbd.cuh: what ONE thread computes for one knot.
+//   kkt_item   : linearised dynamics (A_k, B_k, defect c_{k+1}) + quadraticised tracking cost (Q,q,R,r)
+//                replaces setupKKTSystemBatchedKernel's per-block body (setup_kkt.cuh:52-107),
+//                compute_linearized_dynamics (integrator.cuh:235-257) and
+//                trackingCostGradientAndHessian[_lastblock] (iiwa14_plant.cuh:338-450, indy7_plant.cuh:325-440)
+//   merit_item : cost_k + mu * |defect_k|_1 at z + alpha dz
+//                replaces computeMeritBatchedKernel's per-block body (merit.cuh:36-86), trackingcost
+//                (iiwa14_plant.cuh:275-327) and compute_integrator_error (integrator.cuh:211-233)
+// Outputs are handed to caller-supplied sinks `put(index, value)` so the same code feeds the CUDA kernels
+// (shared-memory transpose staging) and the host unit test.
+#pragma once
+#include "rbd.cuh"
+
+namespace gato {
+
+template<class P>
+struct Items {
+        using R = Rbd<P>;
+        static constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ;
+
+        // ---- tracking cost gradient / Hessian at (x,u) against ref xyz, weight q_cost (see oracle note) ----
+        template<bool WITH_R, class FQ, class Fq, class FR, class Fr>
+        static GATO_HD void cost_grad_hess(const float* xu, const float* ref3, const Costs& cs, FQ&& putQ, Fq&& putq, FR&& putR, Fr&& putr)
+        {
+                float ee[3], J[NQ][3], e[3], h[NQ];
+                R::ee_pos_grad(xu, ee, J);
+                sfor<0, 3>([&](auto rc) { e[rc] = ee[rc] - ref3[rc]; });
+                const float w = cs.q_cost;
+                sfor<0, NQ>([&](auto ic) {
+                        constexpr int i = ic;
+                        float         s = J[i][1] * e[1];
+                        s = fmaf(J[i][0], e[0], s);
+                        h[i] = fmaf(J[i][2], e[2], s);
+                });
+                float bq[NQ], bv[NQ], bu[NQ];  // barrier gradients
+                sfor<0, NQ>([&](auto ic) {
+                        constexpr int i = ic;
+                        bq[i] = R::joint_barrier_grad(xu[i], limit<P, 0, i, 0>(), limit<P, 0, i, 1>());
+                        bv[i] = R::joint_barrier_grad(xu[NQ + i], limit<P, 1, i, 0>(), limit<P, 1, i, 1>());
+                        putq(i, fmaf(h[i], w, cs.q_lim_cost * bq[i]));
+                        putq(NQ + i, fmaf(cs.qd_cost, xu[NQ + i], cs.vel_lim_cost * bv[i]));
+                        if constexpr (WITH_R) {
+                                bu[i] = R::joint_barrier_grad(xu[NX + i], limit<P, 2, i, 0>(), limit<P, 2, i, 1>());
+                                putr(i, fmaf(cs.u_cost, xu[NX + i], cs.ctrl_lim_cost * bu[i]));
+                        }
+                });
+                sfor<0, NX>([&](auto ic) {
+                        constexpr int i = ic;
+                        sfor<0, NX>([&](auto jc) {
+                                constexpr int j = jc;
+                                float         val;
+                                if constexpr (j < NQ && i < NQ) {
+                                        val = (h[i] * h[j]) * w;
+                                        if constexpr (P::ID == 1) {
+                                                if constexpr (i == j) val = fmaf(cs.q_lim_cost, R::joint_barrier_hess(xu[i], limit<P, 0, i, 0>(), limit<P, 0, i, 1>()), val);
+                                        } else {
+                                                val = fmaf(cs.q_lim_cost * bq[i], bq[j], val);
+                                        }
+                                } else if constexpr (i == j) {
+                                        if constexpr (P::ID == 1)
+                                                val = fmaf(cs.vel_lim_cost, R::joint_barrier_hess(xu[i], limit<P, 1, i - NQ, 0>(), limit<P, 1, i - NQ, 1>()), cs.qd_cost);
+                                        else
+                                                val = fmaf(cs.vel_lim_cost * bv[i - NQ], bv[i - NQ], cs.qd_cost);
+                                } else {
+                                        val = 0.0f;
+                                }
+                                putQ(i * NX + j, val);
+                        });
+                });
+                if constexpr (WITH_R) {
+                        sfor<0, NU>([&](auto oc) {
+                                constexpr int o = oc;
+                                sfor<0, NU>([&](auto jc) {
+                                        constexpr int j = jc;
+                                        float         val = 0.0f;
+                                        if constexpr (o == j) {
+                                                if constexpr (P::ID == 1)
+                                                        val = fmaf(cs.ctrl_lim_cost, R::joint_barrier_hess(xu[NX + o], limit<P, 2, o, 0>(), limit<P, 2, o, 1>()), cs.u_cost);
+                                                else
+                                                        val = fmaf(cs.ctrl_lim_cost * bu[o], bu[o], cs.u_cost);
+                                        }
+                                        putR(o * NU + j, val);
+                                });
+                        });
+                }
+        }
+
+        // ---- linearised dynamics: A (NX x NX col-major), B (NX x NU col-major), defect c (NX) -----------------
+        template<class FA, class FB, class Fc>
+        static GATO_HD void linearize(const float* xux, const float* fext, float dt, FA&& putA, FB&& putB, Fc&& putc)
+        {
+                float qdd[NQ], dqdd[3 * NQ * NQ], qn[NQ], qdn[NQ];
+                R::fd_and_grad(xux, xux + NQ, xux + NX, fext, qdd, dqdd);
+                R::integrate(xux, xux + NQ, qdd, dt, qn, qdn);
+                sfor<0, NQ>([&](auto ic) {
+                        constexpr int i = ic;
+                        putc(i, xux[NX + NU + i] - qn[i]);
+                        putc(i + NQ, xux[NX + NU + NQ + i] - qdn[i]);
+                });
+                const float dt_sq_half = (float)((0.5 * (double)dt) * (double)dt);
+                sfor<0, NX * NX>([&](auto ec) {
+                        constexpr int i = ec, c = i / NX, r = i % NX, rd = r % NQ;
+                        const float   d = dqdd[c * NQ + rd];
+                        float         val = (r == c) ? 1.0f : 0.0f;
+                        if constexpr (r < NQ) {
+                                if constexpr (c >= NQ && r == c - NQ) val = val + dt;
+                                val = fmaf(dt_sq_half, d, val);
+                        } else {
+                                val = fmaf(dt, d, val);
+                        }
+                        putA(i, val);
+                });
+                sfor<0, NX * NU>([&](auto ec) {
+                        constexpr int i = ec, c = i / NX, r = i % NX, rd = r % NQ;
+                        const float   d = dqdd[NX * NQ + c * NQ + rd];
+                        putB(i, (r < NQ) ? (dt_sq_half * d) : (dt * d));
+                });
+        }
+
+        // ---- merit contribution of knot k ------------------------------------------------------------------
+        // xux = z + alpha dz at knot k: x_k,u_k,x_{k+1} (k < N-1) or x_{N-1} only; x0err = |x_0 + alpha dz_0 - x_s| entries (used at k = N-1)
+        template<bool LAST>
+        static GATO_HD float tracking_cost(const float* xu, const float* ref3, const Costs& cs)
+        {
+                constexpr int TN = NQ + (LAST ? 0 : NU);
+                float         cv[TN + 3], ee[3];
+                R::ee_pos(xu, ee);
+                sfor<0, NQ>([&](auto ic) {
+                        constexpr int i = ic;
+                        const float   err = xu[i + NQ];
+                        float         c = ((0.5f * cs.qd_cost) * err) * err;
+                        c = fmaf(cs.q_lim_cost, R::joint_barrier(xu[i], limit<P, 0, i, 0>(), limit<P, 0, i, 1>()), c);
+                        c = fmaf(cs.vel_lim_cost, R::joint_barrier(xu[i + NQ], limit<P, 1, i, 0>(), limit<P, 1, i, 1>()), c);
+                        cv[i] = c;
+                });
+                if constexpr (!LAST) {
+                        sfor<0, NU>([&](auto jc) {
+                                constexpr int j = jc;
+                                const float   err = xu[NX + j];
+                                float         c = ((0.5f * cs.u_cost) * err) * err;
+                                c = fmaf(cs.ctrl_lim_cost, R::joint_barrier(xu[NX + j], limit<P, 2, j, 0>(), limit<P, 2, j, 1>()), c);
+                                cv[NQ + j] = c;
+                        });
+                }
+                const float w = LAST ? cs.N_cost : cs.q_cost;
+                sfor<0, 3>([&](auto ic) {
+                        constexpr int i = ic;
+                        const float   err = ee[i] - ref3[i];
+                        cv[TN + i] = (float)((((double)w * 0.5) * (double)err) * (double)err);
+                });
+                return tree_reduce<TN + 3>(cv);
+        }
+        static GATO_HD float merit_mid(const float* xux, const float* ref3, float mu, const float* fext, float dt, const Costs& cs)
+        {
+                const float cost = tracking_cost<false>(xux, ref3, cs);
+                float       qdd[NQ], qn[NQ], qdn[NQ], err[NX];
+                R::forward_dynamics(xux, xux + NQ, xux + NX, fext, qdd);
+                R::integrate(xux, xux + NQ, qdd, dt, qn, qdn);
+                sfor<0, NQ>([&](auto ic) {
+                        constexpr int i = ic;
+                        err[i] = fabsf(xux[NX + NU + i] - qn[i]);
+                        err[i + NQ] = fabsf(xux[NX + NU + NQ + i] - qdn[i]);
+                });
+                const float cons = tree_reduce<NX>(err);
+                return fmaf(mu, cons, cost);
+        }
+        static GATO_HD float merit_last(const float* x, const float* ref3, float mu, const float* x0err, const Costs& cs)
+        {
+                const float cost = tracking_cost<true>(x, ref3, cs);
+                float       err[NX];
+                sfor<0, NX>([&](auto ic) { err[ic] = x0err[ic]; });
+                const float cons = tree_reduce<NX>(err);
+                return fmaf(mu, cons, cost);
+        }
+};
+
+}  // namespace gato

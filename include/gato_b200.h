@@ -1,0 +1,110 @@
+/* gato_b200 — C ABI of the B200-native batched SQP (BSQP) solve path.
+ *
+ * Drop-in boundary for A2R-Lab/GATO's solver object.  Each entry point names the reference interface it
+ * replaces (paths relative to the reference repository root):
+ *
+ *   gato_create / gato_destroy      BSQP<T,BatchSize>::BSQP(...) / ~BSQP()        gato/bsqp/bsqp.cuh:24-61, 200-297
+ *                                   (plant and KNOT_POINTS, compile-time macros in the reference —
+ *                                    CMakeLists.txt:71-75 — are runtime selectors here; BatchSize is runtime)
+ *   gato_solve                      BSQP::solve(T* d_xu, ProblemInputs)            gato/bsqp/bsqp.cuh:103-197
+ *   gato_solve_host                 PyBSQP::solve (H2D, solve, D2H, stats)         python/bindings.cu:68-148
+ *   gato_set_batch                  set_f_ext_batch / set_rho_penalty_batch / set_drho_batch /
+ *                                   set_mu_batch / set_pcg_tol_batch               gato/bsqp/bsqp.cuh:63-79
+ *   gato_reset                      reset_dual / reset_rho                         gato/bsqp/bsqp.cuh:81-87
+ *   gato_set_rho_adaptation         set_rho_adaptation                             gato/bsqp/bsqp.cuh:89
+ *   gato_sim_forward(_host)         BSQP::sim_forward / PyBSQP::sim_forward        gato/bsqp/bsqp.cuh:91, python/bindings.cu:180-194
+ *   gato_get_merits                 copy_final_merit_to_host / copy_initial_merit0_to_host  gato/bsqp/bsqp.cuh:93-101
+ *   gato_stats (struct)             SQPStats / PCGStats / LineSearchStats          gato/types.cuh:23-59
+ *
+ * Conventions: fp32; all layouts are the reference's external layouts: xu[B][(nx+nu)N-nu],
+ * x_s[B][nx], ref[B][6N].  Pointers named d_* are DEVICE pointers on the solver's device, h_* are HOST pointers.
+ * Every function returns 0 on success or a negative gato_status; gato_last_error() gives the message.
+ * There is NO CPU fallback: if no CUDA device / kernel image is available the calls fail with GATO_ERR_CUDA.
+ */
+#ifndef GATO_B200_H
+#define GATO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gato_solver gato_solver;
+
+enum gato_plant { GATO_PLANT_INDY7 = 0, GATO_PLANT_IIWA14 = 1 };
+enum gato_status { GATO_OK = 0, GATO_ERR_ARG = -1, GATO_ERR_CUDA = -2, GATO_ERR_UNSUPPORTED = -3 };
+enum gato_batch_field { GATO_F_EXT = 0, GATO_RHO = 1, GATO_DRHO = 2, GATO_MU = 3, GATO_PCG_TOL = 4 };
+enum gato_reset_field { GATO_RESET_DUAL = 0, GATO_RESET_RHO = 1 };
+
+/* Constructor scalars, in the reference's constructor order (bsqp.cuh:43). */
+typedef struct gato_params {
+        float    dt;
+        uint32_t max_sqp_iters;
+        float    kkt_tol;
+        uint32_t max_pcg_iters;
+        float    pcg_tol;
+        float    solve_ratio;
+        float    mu;
+        float    q_cost, qd_cost, u_cost, N_cost, q_lim_cost, vel_lim_cost, ctrl_lim_cost;
+        float    rho;
+} gato_params;
+
+/* Per-solve statistics; buffers are owned by the solver and valid until the next gato_solve*/
+typedef struct gato_stats {
+        double         solve_time_us;   /* host wall clock around the solve, like bsqp.cuh:109,185-190 */
+        float          device_time_ms;  /* CUDA-event time of the device work on the solver stream */
+        int32_t        batch;
+        int32_t        n_pcg;           /* PCG solves performed (= outer iterations executed) */
+        int32_t        n_ls;            /* line searches performed (n_pcg or n_pcg-1, bsqp.cuh:165 vs :176) */
+        const int32_t* sqp_iters;       /* [B] */
+        const int32_t* kkt_converged;   /* [B] */
+        const int32_t* pcg_iters;       /* [n_pcg][B] */
+        const float*   ls_min_merit;    /* [n_ls][B] */
+        const float*   ls_step_size;    /* [n_ls][B], -1 = rejected */
+        const float*   final_merit;     /* [B] */
+        const float*   initial_merit;   /* [B] */
+} gato_stats;
+
+/* stream: a cudaStream_t (as void*) or NULL for a solver-owned non-blocking stream. */
+int  gato_create(gato_solver** out, int plant, int knot_points, int batch, int device, void* stream, const gato_params* params);
+void gato_destroy(gato_solver* s);
+const char* gato_last_error(const gato_solver* s); /* s may be NULL: last creation error */
+
+int gato_set_batch(gato_solver* s, int field, const float* h_values, int set_as_reset_default);
+int gato_reset(gato_solver* s, int field);
+int gato_set_rho_adaptation(gato_solver* s, int enabled);
+
+/* Solve in place on device memory (synchronous, like the reference). */
+int gato_solve(gato_solver* s, float* d_xu, const float* d_x_s, const float* d_ref, float timestep, gato_stats* stats);
+/* Same through host buffers: H2D of xu/x_s/ref, solve, D2H of xu. */
+int gato_solve_host(gato_solver* s, float* h_xu, const float* h_x_s, const float* h_ref, float timestep, gato_stats* stats);
+/* Asynchronous pair for multi-GPU drivers: enqueue on the solver stream, then collect. */
+int gato_solve_async(gato_solver* s, float* d_xu, const float* d_x_s, const float* d_ref, float timestep);
+int gato_solve_wait(gato_solver* s, gato_stats* stats);
+
+int gato_sim_forward(gato_solver* s, float* d_xkp1 /*[B][nx]*/, const float* d_xk /*[nx]*/, const float* d_uk /*[nu]*/, float dt);
+int gato_sim_forward_host(gato_solver* s, float* h_xkp1, const float* h_xk, const float* h_uk, float dt);
+int gato_get_merits(gato_solver* s, float* h_final /*[B] or NULL*/, float* h_initial /*[B] or NULL*/);
+
+/* Introspection */
+int  gato_dims(int plant, int knot_points, int* nx, int* nu, int* traj_size);
+long gato_kernel_launches(const gato_solver* s); /* kernels launched by this solver so far */
+int  gato_get_device_pointers(gato_solver* s, float** d_xu, float** d_x_s, float** d_ref); /* solver-owned staging buffers used by *_host calls */
+
+/* Stage-level entry points (host buffers; used by the parity tests, same layouts as the reference kernels'
+ * global buffers — setup_kkt.cuh:15, schur_linsys.cuh:14/214/316, pcg.cuh:14, merit.cuh:17, line_search.cuh:13). */
+int gato_stage_kkt(int plant, int N, int B, const float* xu, const float* xs, const float* ref, const float* fext, float dt, const float* cost7, float* Q, float* R, float* q, float* r, float* A,
+                   float* Bm, float* c);
+int gato_stage_schur(int plant, int N, int B, float* Q, float* R, const float* q, const float* r, const float* A, const float* Bm, const float* c, const float* rho, float* S, float* Pinv,
+                     float* gamma);
+int gato_stage_pcg(int plant, int N, int B, const float* S, const float* Pinv, const float* gamma, float* lambda, const float* eps, int max_iters, const int* kkt_conv, int* iters);
+int gato_stage_dz(int plant, int N, int B, const float* lambda, const float* Qinv, const float* Rinv, float* q, float* r, const float* A, const float* Bm, float* dz);
+int gato_stage_merit(int plant, int N, int B, const float* xu, const float* dz, const float* xs, const float* ref, const float* mu, const float* fext, float dt, const float* cost7, int num_alphas,
+                     float* merit);
+int gato_stage_linesearch(int plant, int N, int B, float* xu, const float* dz, const float* merit8, float* merit_init, float* step, float* rho, float* drho, int adapt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GATO_B200_H */

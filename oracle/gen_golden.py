@@ -107,6 +107,22 @@ def gen_for_lib(plant, N, mode, cfg, out_dir, keep=2):
             if key in ws["extra"]:
                 sv.set_batch(key, ws["extra"][key])
         o1 = sv.solve(ws["xu"], ws["xs"], ws["ref"], ws["dt"])
+        if Bs <= 64:
+            # run-to-run determinism of the reference (its Schur kernel 1 races on d_Q): repeat on fresh
+            # solver objects and record, per solve, how many repeats reproduce the first run bit-for-bit
+            same = np.zeros(Bs, np.int32)
+            reps = 5
+            for _ in range(reps):
+                sx = be.solver(Bs, ps)
+                for key in ("rho", "mu"):
+                    if key in ws["extra"]:
+                        sx.set_batch(key, ws["extra"][key])
+                ox = sx.solve(ws["xu"], ws["xs"], ws["ref"], ws["dt"])
+                same += (ox["XU"] == o1["XU"]).all(axis=1).astype(np.int32)
+                sx.close()
+            G[f"solve_B{Bs}_a_repro_count"] = same
+            G[f"solve_B{Bs}_a_repro_reps"] = np.int32(reps)
+            print("  determinism B", Bs, "solves reproduced in all repeats:", int((same == reps).sum()), "/", Bs, flush=True)
         # second solve WITHOUT reset, warm-started from the first result: pins lambda/rho persistence (bsqp.cuh:81-87,189)
         o2 = sv.solve(o1["XU"], ws["xs"], ws["ref"], ws["dt"])
         tag = f"solve_B{Bs}_"
@@ -185,12 +201,18 @@ def main():
         meta["gpu"] = f"unknown ({e})"
     (out / "meta.json").write_text(json.dumps(meta, indent=1))
     for plant, N, mode, cfg in LIBS:
-        if a.only and a.only not in f"{plant}_N{N}_{mode}":
-            continue
-        try:
-            gen_for_lib(plant, N, mode, cfg, out, keep=1 if N >= 128 else 2)
-        except FileNotFoundError as e:
-            print("skip (not built):", e, flush=True)
+        name = f"{plant}_N{N}_{mode}"
+        if a.only:
+            if a.only != name:
+                continue
+            try:
+                gen_for_lib(plant, N, mode, cfg, out, keep=1 if N >= 128 else 2)
+            except FileNotFoundError as e:
+                print("skip (not built):", e, flush=True)
+        else:
+            # one process per library: a CUDA fault in the reference (e.g. the indy7 merit kernel) must not poison the rest
+            rc = subprocess.call([sys.executable, __file__, "--out", str(out), "--only", name])
+            print("lib", name, "exit", rc, flush=True)
     if a.timing:
         timing(out)
 
