@@ -42,7 +42,7 @@ struct Ctx {
         float *      ls_merit_log, *ls_step_log;  // [max_sqp_iters][B]
 };
 
-enum : int { F_K2 = 1, F_PCG = 2, F_DZ = 4, F_WRITE_P = 8, F_MERIT = 16, F_LS = 32, F_BOOK = 64, F_CHECK_STOP = 128 };
+enum : int { F_K2 = 1, F_PCG = 2, F_DZ = 4, F_WRITE_P = 8, F_MERIT = 16, F_LS = 32, F_BOOK = 64, F_CHECK_STOP = 128, F_ZERO_DZ = 256 };
 
 // true when an iteration j < upto already satisfied the early-exit test of bsqp.cuh:165
 __device__ __forceinline__ bool stopped_before(const Ctx& c, int upto)
@@ -628,6 +628,7 @@ __global__ void __launch_bounds__(NA == 1 ? 128 : 256) k_merit_ls(Ctx c)
         const float*            dz = c.dz + (size_t)b * traj;
         if (c.flags & F_MERIT) {
                 const float mu = c.mu[b];
+                const bool  zero_dz = (c.flags & F_ZERO_DZ) != 0;
                 float       fext[6];
                 sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * b + ic]; });
                 for (int w = tid; w < NA * N; w += T) {
@@ -639,14 +640,14 @@ __global__ void __launch_bounds__(NA == 1 ? 128 : 256) k_merit_ls(Ctx c)
                         const float *xk = xu + (size_t)k * (NX + NU), *dk = dz + (size_t)k * (NX + NU);
                         float        m;
                         if (k < N - 1) {
-                                if constexpr (NA == 1)
+                                if (zero_dz)  // dz == 0 (bsqp.cuh:112,180): z + 1*0 = z, skip the loads
                                         sfor<0, 2 * NX + NU>([&](auto ic) { xux[ic] = xk[ic]; });
                                 else
                                         sfor<0, 2 * NX + NU>([&](auto ic) { xux[ic] = fmaf(alpha, dk[ic], xk[ic]); });
                                 m = Items<P>::merit_mid(xux, ref3, mu, fext, c.dt, c.cs);
                         } else {
                                 float e0[NX];
-                                if constexpr (NA == 1) {
+                                if (zero_dz) {
                                         sfor<0, NX>([&](auto ic) { xux[ic] = xk[ic]; });
                                         sfor<0, NX>([&](auto ic) { e0[ic] = fabsf(xu[ic] - c.xs[(size_t)b * NX + ic]); });
                                 } else {

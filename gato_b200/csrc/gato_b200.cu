@@ -181,7 +181,7 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
         CUDA_TRY(s, cudaMemsetAsync(s->num_solved.p, 0, sizeof(unsigned) * s->max_it, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->pcg_log.p, 0, sizeof(int) * (size_t)s->max_it * B, s->stream));
         // initial merit (dz = 0, alpha = 1)  bsqp.cuh:116-118
-        c.flags = F_MERIT;
+        c.flags = F_MERIT | F_ZERO_DZ;
         launch_merit<P, 1>(s, c);
         CUDA_TRY(s, cudaMemcpyAsync(s->merit0.p, s->merit_cur.p, sizeof(float) * B, cudaMemcpyDeviceToDevice, s->stream));
         for (int it = 0; it < s->max_it; it++) {
@@ -195,7 +195,7 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
                 launch_merit<P, kNumAlphas>(s, c);
         }
         // final merit on the updated trajectory  bsqp.cuh:180-182
-        c.flags = F_MERIT;
+        c.flags = F_MERIT | F_ZERO_DZ;
         launch_merit<P, 1>(s, c);
         CUDA_TRY(s, cudaGetLastError());
         // results -> pinned host buffers
