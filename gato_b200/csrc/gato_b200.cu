@@ -84,6 +84,7 @@ struct gato_solver {
         std::chrono::high_resolution_clock::time_point t_start;
         bool                                           pending = false;
         size_t                                         smem_pcg = 0, smem_schur = 0;
+        int                                            pcg_threads = 0;
 
         gato_solver(int plant_, int N_, int B_, int dev) : plant(plant_), N(N_), B(B_), device(dev), d(plant_ ? 7 : 6, N_), prm{}, max_it(1) {}
 };
@@ -91,28 +92,38 @@ struct gato_solver {
 namespace {
 
 template<class P>
+int pcg_threads(int N)
+{
+        return ((N + 2) * 2 * P::NQ + 31) / 32 * 32;  // one thread per padded vector index (rows are indices nx .. nx + N*nx)
+}
+template<class P>
 size_t pcg_smem_bytes(int N, int threads)
 {
-        constexpr int NX = 2 * P::NQ, W = 3 * NX, WP = (W + 3) / 4 * 4;
-        const size_t  nrows = (size_t)N * NX, n = (size_t)(N + 2) * NX;
-        return sizeof(float) * (2 * nrows * WP + 5 * n + 40 + 64 * (threads / 32) + (size_t)(N - 1) * NX * NX);
+        constexpr int NX = 2 * P::NQ;
+        const size_t  n = (size_t)(N + 2) * NX;
+        return sizeof(float) * (2 * n + 64 + 64 * (threads / 32) + (size_t)N * NX * NX + (size_t)(N - 1) * NX * NX);
 }
 template<class P>
 size_t schur_smem_bytes(int warps)
 {
         return sizeof(SchurSmem<2 * P::NQ, P::NQ>) * warps;
 }
-constexpr int kPcgThreads = 512, kSchurWarps = 4;
+constexpr int kSchurWarps = 4;
 
 template<class P>
 int configure_kernels(gato_solver* s)
 {
-        s->smem_pcg = pcg_smem_bytes<P>(s->N, kPcgThreads);
+        s->pcg_threads = pcg_threads<P>(s->N);
+        if (s->pcg_threads > 512) {
+                s->err = "knot_points too large for the register-resident PCG kernel (needs (N + 2) * nx <= 512)";
+                return GATO_ERR_UNSUPPORTED;
+        }
+        s->smem_pcg = pcg_smem_bytes<P>(s->N, s->pcg_threads);
         s->smem_schur = schur_smem_bytes<P>(kSchurWarps);
         int maxsm = 0;
         CUDA_TRY(s, cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
         if (s->smem_pcg > (size_t)maxsm) {
-                s->err = "knot_points too large for the shared-memory-resident PCG kernel on this device";
+                s->err = "knot_points too large for the PCG kernel's shared memory on this device";
                 return GATO_ERR_UNSUPPORTED;
         }
         CUDA_TRY(s, cudaFuncSetAttribute(k_pcg<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_pcg));
@@ -161,7 +172,7 @@ void launch_schur(gato_solver* s, const Ctx& c)
 template<class P>
 void launch_pcg(gato_solver* s, const Ctx& c)
 {
-        k_pcg<P><<<c.B, kPcgThreads, s->smem_pcg, s->stream>>>(c);
+        k_pcg<P><<<c.B, s->pcg_threads, s->smem_pcg, s->stream>>>(c);
         s->launches++;
 }
 template<class P, int NA>
