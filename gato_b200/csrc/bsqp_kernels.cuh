@@ -22,6 +22,9 @@
 
 namespace gato {
 
+#ifndef GATO_MERIT_MIN_BLOCKS
+#define GATO_MERIT_MIN_BLOCKS 2
+#endif
 constexpr int   kNumAlphas = 8;                                                         // settings.h:15
 constexpr float kRhoInit = 1e-3f, kRhoFactor = 1.2f, kRhoMin = 1e-8f, kRhoMax = 10.0f;  // settings.h:18-21
 constexpr int   kPcgRefThreads = 1024;  // settings.h:25 — fixes the shape of the reference's dot-product tree
@@ -54,77 +57,84 @@ __device__ __forceinline__ bool stopped_before(const Ctx& c, int upto)
 }
 
 // =====================================================================================================
-// k_kkt: one thread per (solve, knot).  Knot N-1 is the "terminal" item: Q_{N-1}, q_{N-1} evaluated at
-// x_{N-2} against ref_{N-1} (setup_kkt.cuh:83-100) and c_0 = x_0 - x_s; it runs the same cost code as the
-// other lanes, so a warp (= one solve when N = 32) does not diverge in the cost part.
-// Results are transposed through shared memory so that HBM/L2 stores are coalesced per knot block.
+// k_kkt: one thread per work item, three kinds of items in separate warps (blockIdx.y = kind) so that no warp diverges:
+//   kind 0  cost blocks of knot k = 0..N-1 (Q,q,R,r); knot N-1 is the "terminal" item: Q_{N-1}, q_{N-1} evaluated at
+//           x_{N-2} against ref_{N-1} (setup_kkt.cuh:83-100) and c_0 = x_0 - x_s
+//   kind 1  linearised dynamics of knot k = 0..N-2, d/dq half: columns 0..nq-1 of A_k and the defect c_{k+1}
+//   kind 2  d/dqd half: columns nq..nx-1 of A_k and B_k
+// (The two dynamics halves repeat the M^-1 / RNEA prologue; splitting doubles the parallelism of what is a latency-bound
+// kernel at batch 512.)  Results are transposed through shared memory so that HBM/L2 stores are coalesced per knot block.
 // =====================================================================================================
 template<class P>
 __global__ void __launch_bounds__(32) k_kkt(Ctx c)
 {
         constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ, ST = 33;
-        constexpr int ROWS = NX * NX + NX * NU + NX;  // A | B | c  (the cost pass uses fewer rows)
+        constexpr int ROWS = NX * NX + NX + NU * NU + NU + NX;  // kind 0 needs the most rows: Q | q | R | r | c0
         if (stopped_before(c, c.it)) return;
         __shared__ float stage[ROWS * ST];
+        const int        kind = blockIdx.y;
         const int        lane = threadIdx.x;
         const int        item0 = blockIdx.x * 32;
-        const int        total = c.B * c.N;
-        const int        item = item0 + lane;
-        const bool       valid = item < total;
-        const int        b = valid ? item / c.N : 0, k = valid ? item % c.N : 0;
-        const bool       term = (k == c.N - 1);
-        const int        traj = (NX + NU) * c.N - NU;
-        const int        ks = term ? k - 1 : k;  // knot whose (x,u) this item evaluates
-        float            xux[2 * NX + NU];
+        const int        per = (kind == 0) ? c.N : c.N - 1;  // items per solve
+        const int        total = c.B * per;
+        if (item0 >= total) return;
+        const int  item = item0 + lane;
+        const bool valid = item < total;
+        const int  b = valid ? item / per : 0, k = valid ? item % per : 0;
+        const bool term = (kind == 0) && (k == c.N - 1);
+        const int  traj = (NX + NU) * c.N - NU;
+        const int  ks = term ? k - 1 : k;  // knot whose (x,u) this item evaluates
+        float      xux[2 * NX + NU];
         {
                 const float* src = c.xu + (size_t)b * traj + (size_t)ks * (NX + NU);
                 sfor<0, 2 * NX + NU>([&](auto ic) { xux[ic] = src[ic]; });
         }
-        float fext[6], ref3[3];
-        sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * b + ic]; });
-        sfor<0, 3>([&](auto ic) { ref3[ic] = c.ref[(size_t)b * 6 * c.N + 6 * k + ic]; });
-
-        // write staged rows [row0, row0+count) of every selected item to dst[(b*N + knot + koff)*count + e]
-        auto flush = [&](float* dst, int row0, int count, int koff, int which /*0 mid items, 1 terminal items, 2 all*/) {
+        // write staged rows [row0, row0+count) of every selected item to dst[(b*N + knot + koff)*stride + off + e]
+        auto flush = [&](float* dst, int row0, int count, int stride, int off, int koff, int which /*0 non-terminal, 1 terminal, 2 all*/) {
                 const int nvalid = min(32, total - item0);
                 for (int i = 0; i < nvalid; i++) {
-                        const int  it_ = item0 + i, bi = it_ / c.N, ki = it_ % c.N;
-                        const bool ti = (ki == c.N - 1);
+                        const int  it_ = item0 + i, bi = it_ / per, ki = it_ % per;
+                        const bool ti = (kind == 0) && (ki == c.N - 1);
                         if ((which == 0 && ti) || (which == 1 && !ti)) continue;
-                        float* d = dst + ((size_t)bi * c.N + ki + koff) * count;
+                        float* d = dst + ((size_t)bi * c.N + ki + koff) * stride + off;
                         for (int e = lane; e < count; e += 32) d[e] = stage[(row0 + e) * ST + i];
                 }
         };
-        constexpr int rQ = 0, rq = NX * NX, rR = rq + NX, rr = rR + NU * NU, rc0 = rr + NU;
-        static_assert(rc0 + NX <= ROWS, "stage too small");
-
-        // ---- cost blocks ----
-        Items<P>::template cost_grad_hess<true>(
-            xux, ref3, c.cs, [&](int e, float v) { stage[(rQ + e) * ST + lane] = v; }, [&](int e, float v) { stage[(rq + e) * ST + lane] = v; },
-            [&](int e, float v) { stage[(rR + e) * ST + lane] = v; }, [&](int e, float v) { stage[(rr + e) * ST + lane] = v; });
-        if (term && valid) {
-                const float* x0 = c.xu + (size_t)b * traj;
-                sfor<0, NX>([&](auto ic) { stage[(rc0 + ic) * ST + lane] = x0[ic] - c.xs[(size_t)b * NX + ic]; });
+        if (kind == 0) {
+                float ref3[3];
+                sfor<0, 3>([&](auto ic) { ref3[ic] = c.ref[(size_t)b * 6 * c.N + 6 * k + ic]; });
+                constexpr int rQ = 0, rq = NX * NX, rR = rq + NX, rr = rR + NU * NU, rc0 = rr + NU;
+                Items<P>::template cost_grad_hess<true>(
+                    xux, ref3, c.cs, [&](int e, float v) { stage[(rQ + e) * ST + lane] = v; }, [&](int e, float v) { stage[(rq + e) * ST + lane] = v; },
+                    [&](int e, float v) { stage[(rR + e) * ST + lane] = v; }, [&](int e, float v) { stage[(rr + e) * ST + lane] = v; });
+                if (term && valid) {
+                        const float* x0 = c.xu + (size_t)b * traj;
+                        sfor<0, NX>([&](auto ic) { stage[(rc0 + ic) * ST + lane] = x0[ic] - c.xs[(size_t)b * NX + ic]; });
+                }
+                __syncwarp();
+                flush(c.Q, rQ, NX * NX, NX * NX, 0, 0, 2);
+                flush(c.q, rq, NX, NX, 0, 0, 2);
+                flush(c.R, rR, NU * NU, NU * NU, 0, 0, 0);
+                flush(c.r, rr, NU, NU, 0, 0, 0);
+                flush(c.c, rc0, NX, NX, 0, -(c.N - 1), 1);
+        } else {
+                float fext[6];
+                sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * b + ic]; });
+                constexpr int rA = 0, rX = NX * NQ;  // half of A (NX*NQ contiguous floats), then c (kind 1) or B (kind 2)
+                if (kind == 1) {
+                        Items<P>::template linearize_half<0>(
+                            xux, fext, c.dt, [&](int e, float v) { stage[(rA + e) * ST + lane] = v; }, [&](int, float) {}, [&](int e, float v) { stage[(rX + e) * ST + lane] = v; });
+                        __syncwarp();
+                        flush(c.A, rA, NX * NQ, NX * NX, 0, 0, 2);
+                        flush(c.c, rX, NX, NX, 0, 1, 2);
+                } else {
+                        Items<P>::template linearize_half<1>(
+                            xux, fext, c.dt, [&](int e, float v) { stage[(rA + e - NX * NQ) * ST + lane] = v; }, [&](int e, float v) { stage[(rX + e) * ST + lane] = v; }, [&](int, float) {});
+                        __syncwarp();
+                        flush(c.A, rA, NX * NQ, NX * NX, NX * NQ, 0, 2);
+                        flush(c.Bm, rX, NX * NU, NX * NU, 0, 0, 2);
+                }
         }
-        __syncwarp();
-        flush(c.Q, rQ, NX * NX, 0, 2);
-        flush(c.q, rq, NX, 0, 2);
-        flush(c.R, rR, NU * NU, 0, 0);
-        flush(c.r, rr, NU, 0, 0);
-        flush(c.c, rc0, NX, -(c.N - 1), 1);
-        __syncwarp();
-
-        // ---- linearised dynamics (the terminal lane idles) ----
-        constexpr int rA = 0, rB = NX * NX, rc = rB + NX * NU;
-        if (!term && valid) {
-                Items<P>::linearize(
-                    xux, fext, c.dt, [&](int e, float v) { stage[(rA + e) * ST + lane] = v; }, [&](int e, float v) { stage[(rB + e) * ST + lane] = v; },
-                    [&](int e, float v) { stage[(rc + e) * ST + lane] = v; });
-        }
-        __syncwarp();
-        flush(c.A, rA, NX * NX, 0, 0);
-        flush(c.Bm, rB, NX * NU, 0, 0);
-        flush(c.c, rc, NX, 1, 0);
 }
 
 #include "bsqp_linalg_kernels.cuh"  // k_schur, k_pcg
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(32) k_kkt(Ctx c)
 // NA = 8: merit at z + 2^-a dz for a = 0..7, then the line search.  NA = 1: merit at z (initial / final merit).
 // =====================================================================================================
 template<class P, int NA>
-__global__ void __launch_bounds__(NA == 1 ? 128 : 256) k_merit_ls(Ctx c)
+__global__ void __launch_bounds__(NA == 1 ? 128 : 256, NA == 1 ? 1 : GATO_MERIT_MIN_BLOCKS) k_merit_ls(Ctx c)
 {
         constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ;
         if (NA > 1 && stopped_before(c, c.it + 1)) return;  // the iteration that meets the test skips merit + line search (bsqp.cuh:165)

@@ -158,8 +158,8 @@ inline int merit_threads(int na, int N)
 template<class P>
 void launch_kkt(gato_solver* s, const Ctx& c)
 {
-        const int items = c.B * c.N;
-        k_kkt<P><<<(items + 31) / 32, 32, 0, s->stream>>>(c);
+        const int items = c.B * c.N;  // kind 0 has B*N items, kinds 1 and 2 have B*(N-1)
+        k_kkt<P><<<dim3((items + 31) / 32, 3), 32, 0, s->stream>>>(c);
         s->launches++;
 }
 template<class P>

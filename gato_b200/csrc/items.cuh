@@ -117,6 +117,46 @@ struct Items {
                 });
         }
 
+        // ---- the same linearisation split in two halves that different threads compute (each repeats the prologue) ----------
+        //   HALF 0: columns 0..NQ-1 of A (d/dq) and the defect c          HALF 1: columns NQ..NX-1 of A (d/dqd) and B
+        // putA receives indices of the full col-major A; results are bit-identical to linearize().
+        template<int HALF, class FA, class FB, class Fc>
+        static GATO_HD void linearize_half(const float* xux, const float* fext, float dt, FA&& putA, FB&& putB, Fc&& putc)
+        {
+                typename R::DynState st;
+                R::dyn_prologue(xux, xux + NQ, xux + NX, fext, st);
+                const float dt_sq_half = (float)((0.5 * (double)dt) * (double)dt);
+                float       blk[NQ * NQ];
+                R::template grad_block<HALF>(st, xux + NQ, blk);
+                sfor<0, NX * NQ>([&](auto ec) {
+                        constexpr int e = ec, cl = e / NX, r = e % NX, rd = r % NQ, c = cl + HALF * NQ;
+                        const float   d = blk[cl * NQ + rd];
+                        float         val = (r == c) ? 1.0f : 0.0f;
+                        if constexpr (r < NQ) {
+                                if constexpr (c >= NQ && r == c - NQ) val = val + dt;
+                                val = fmaf(dt_sq_half, d, val);
+                        } else {
+                                val = fmaf(dt, d, val);
+                        }
+                        putA(c * NX + r, val);
+                });
+                if constexpr (HALF == 0) {
+                        float qn[NQ], qdn[NQ];
+                        R::integrate(xux, xux + NQ, st.qdd, dt, qn, qdn);
+                        sfor<0, NQ>([&](auto ic) {
+                                constexpr int i = ic;
+                                putc(i, xux[NX + NU + i] - qn[i]);
+                                putc(i + NQ, xux[NX + NU + NQ + i] - qdn[i]);
+                        });
+                } else {
+                        sfor<0, NX * NU>([&](auto ec) {
+                                constexpr int i = ec, c = i / NX, r = i % NX, rd = r % NQ;
+                                const float   d = R::template minv_sym<rd, c>(st.Minv);
+                                putB(i, (r < NQ) ? (dt_sq_half * d) : (dt * d));
+                        });
+                }
+        }
+
         // ---- merit contribution of knot k ------------------------------------------------------------------
         // xux = z + alpha dz at knot k: x_k,u_k,x_{k+1} (k < N-1) or x_{N-1} only; x0err = |x_0 + alpha dz_0 - x_s| entries (used at k = N-1)
         template<bool LAST>

@@ -453,49 +453,64 @@ struct Rbd {
                 sfor<0, NQ>([&](auto jc) { dc[jc] = df[jc][2]; });
         }
 
-        // forwardDynamicsAndGradient with wrench (iiwa14_plant.cuh:229-268):
-        // dqdd col-major NQ x 3NQ = [ dqdd/dq | dqdd/dqd | Minv ]
-        static GATO_HD void fd_and_grad(const float* q, const float* qd, const float* u, const float* fext, float (&qdd)[NQ], float (&dqdd)[3 * NQ * NQ])
+        // forwardDynamicsAndGradient with wrench (iiwa14_plant.cuh:229-268), split so that the column blocks of the gradient can be
+        // computed by different threads: dyn_prologue (X, M^-1, RNEA, qdd, RNEA with qdd, I v, fx(v) I) + grad_block<W>.
+        struct DynState {
+                Xmat  X;
+                float Minv[NQ * NQ];
+                V6    v, a, f, Iv;
+                float FxvI[NQ][36];
+                float qdd[NQ];
+        };
+        static GATO_HD void dyn_prologue(const float* q, const float* qd, const float* u, const float* fext, DynState& st)
         {
                 float t[2 * NQ];
-                Xmat  X;
                 sincos(q, t);
-                update_X(t, X);
-                float Minv[NQ * NQ];
-                minv(X, Minv);
-                V6 v, a, f;
-                rnea<false>(X, qd, nullptr, fext, v, a, f);
-                fd_finish(Minv, u, f, qdd);
-                rnea<true>(X, qd, qdd, fext, v, a, f);
-                V6    Iv;
-                float FxvI[NQ][36];
+                update_X(t, st.X);
+                minv(st.X, st.Minv);
+                rnea<false>(st.X, qd, nullptr, fext, st.v, st.a, st.f);
+                fd_finish(st.Minv, u, st.f, st.qdd);
+                rnea<true>(st.X, qd, st.qdd, fext, st.v, st.a, st.f);
                 sfor<0, NQ>([&](auto jc) {
                         constexpr int j = jc;
-                        sfor<0, 6>([&](auto rc) { Iv[j][rc] = irow<j, rc>(v[j]); });
+                        sfor<0, 6>([&](auto rc) { st.Iv[j][rc] = irow<j, rc>(st.v[j]); });
                         sfor<0, 6>([&](auto cc) {
                                 constexpr int c = cc;
                                 float         col[6], out[6];
                                 sfor<0, 6>([&](auto tc) { col[tc] = inertia<P, j, tc, c>(); });
-                                fx_times_v(out, v[j], col);
-                                sfor<0, 6>([&](auto rc) { FxvI[j][6 * c + rc] = out[rc]; });
+                                fx_times_v(out, st.v[j], col);
+                                sfor<0, 6>([&](auto rc) { st.FxvI[j][6 * c + rc] = out[rc]; });
                         });
                 });
-                sfor<0, 2>([&](auto wc) {
-                        constexpr int w = wc;
-                        sfor<0, NQ>([&](auto kc) {
-                                constexpr int k = kc;
-                                float         dc[NQ];
-                                rnea_grad_col<w, k>(X, qd, v, a, f, Iv, FxvI, dc);
-                                // dqdd[:, col] = -Minv * dc   (symmetric-upper lookup)
-                                sfor<0, NQ>([&](auto rc) {
-                                        constexpr int row = rc;
-                                        float         val = 0.0f;
-                                        sfor<0, NQ>([&](auto cc) { val = fmaf(minv_sym<row, cc>(Minv), dc[cc], val); });
-                                        dqdd[w * NQ * NQ + k * NQ + row] = -val;
-                                });
+        }
+        // W = 0: d qdd / dq, W = 1: d qdd / dqd;  out[k*NQ + row] = -(Minv * dc_k)[row]  (symmetric-upper lookup, plant:249-259)
+        template<int W>
+        static GATO_HD void grad_block(const DynState& st, const float* qd, float (&out)[NQ * NQ])
+        {
+                sfor<0, NQ>([&](auto kc) {
+                        constexpr int k = kc;
+                        float         dc[NQ];
+                        rnea_grad_col<W, k>(st.X, qd, st.v, st.a, st.f, st.Iv, st.FxvI, dc);
+                        sfor<0, NQ>([&](auto rc) {
+                                constexpr int row = rc;
+                                float         val = 0.0f;
+                                sfor<0, NQ>([&](auto cc) { val = fmaf(minv_sym<row, cc>(st.Minv), dc[cc], val); });
+                                out[k * NQ + row] = -val;
                         });
                 });
-                sfor<0, NQ * NQ>([&](auto ec) { dqdd[2 * NQ * NQ + ec] = minv_sym<ec % NQ, ec / NQ>(Minv); });
+        }
+        // dqdd col-major NQ x 3NQ = [ dqdd/dq | dqdd/dqd | Minv ]
+        static GATO_HD void fd_and_grad(const float* q, const float* qd, const float* u, const float* fext, float (&qdd)[NQ], float (&dqdd)[3 * NQ * NQ])
+        {
+                DynState st;
+                dyn_prologue(q, qd, u, fext, st);
+                sfor<0, NQ>([&](auto ic) { qdd[ic] = st.qdd[ic]; });
+                float blk[NQ * NQ];
+                grad_block<0>(st, qd, blk);
+                sfor<0, NQ * NQ>([&](auto ec) { dqdd[ec] = blk[ec]; });
+                grad_block<1>(st, qd, blk);
+                sfor<0, NQ * NQ>([&](auto ec) { dqdd[NQ * NQ + ec] = blk[ec]; });
+                sfor<0, NQ * NQ>([&](auto ec) { dqdd[2 * NQ * NQ + ec] = minv_sym<ec % NQ, ec / NQ>(st.Minv); });
         }
 
         // ---- end-effector position and positional Jacobian ---------------------------------------------
