@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "../../include/gato_b200.h"
-#include "bsqp_kernels.cuh"
+#include "launchers.h"
 
 using namespace gato;
 
@@ -84,7 +84,7 @@ struct gato_solver {
         std::chrono::high_resolution_clock::time_point t_start;
         bool                                           pending = false;
         size_t                                         smem_pcg = 0, smem_schur = 0;
-        int                                            pcg_threads = 0;
+        int                                            pcg_threads = 0, pcg_rpt = 0;
 
         gato_solver(int plant_, int N_, int B_, int dev) : plant(plant_), N(N_), B(B_), device(dev), d(plant_ ? 7 : 6, N_), prm{}, max_it(1) {}
 };
@@ -104,30 +104,30 @@ size_t pcg_smem_bytes(int N, int threads)
         return sizeof(float) * (2 * n + 64 + 64 * (threads / 32) + (size_t)N * NX * NX + (size_t)(N - 1) * NX * NX);
 }
 template<class P>
-size_t schur_smem_bytes(int warps)
-{
-        return sizeof(SchurSmem<2 * P::NQ, P::NQ>) * warps;
-}
-constexpr int kSchurWarps = 4;
-
-template<class P>
 int configure_kernels(gato_solver* s)
 {
         s->pcg_threads = pcg_threads<P>(s->N);
+        s->pcg_rpt = 0;  // 0: register-resident kernel (one thread per padded index); >0: streaming kernel, indices per thread
         if (s->pcg_threads > 512) {
-                s->err = "knot_points too large for the register-resident PCG kernel (needs (N + 2) * nx <= 512)";
-                return GATO_ERR_UNSUPPORTED;
+                const int n = (s->N + 2) * 2 * P::NQ;
+                s->pcg_rpt = (n + 1023) / 1024;
+                if (s->pcg_rpt > 4) {
+                        s->err = "knot_points too large (the streaming PCG kernel supports (N + 2) * nx <= 4096)";
+                        return GATO_ERR_UNSUPPORTED;
+                }
+                s->pcg_threads = 1024;
+                s->smem_pcg = sizeof(float) * ((size_t)2 * n + 64 + 64 * 32 + (size_t)(s->N - 1) * 4 * P::NQ * P::NQ);
+        } else {
+                s->smem_pcg = pcg_smem_bytes<P>(s->N, s->pcg_threads);
         }
-        s->smem_pcg = pcg_smem_bytes<P>(s->N, s->pcg_threads);
-        s->smem_schur = schur_smem_bytes<P>(kSchurWarps);
+        s->smem_schur = schur_smem_bytes<P>();
         int maxsm = 0;
         CUDA_TRY(s, cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
         if (s->smem_pcg > (size_t)maxsm) {
                 s->err = "knot_points too large for the PCG kernel's shared memory on this device";
                 return GATO_ERR_UNSUPPORTED;
         }
-        CUDA_TRY(s, cudaFuncSetAttribute(k_pcg<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_pcg));
-        CUDA_TRY(s, cudaFuncSetAttribute(k_schur<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_schur));
+        CUDA_TRY(s, configure_linalg<P>(s->pcg_rpt, s->smem_pcg, s->smem_schur));
         return GATO_OK;
 }
 
@@ -147,38 +147,28 @@ Ctx make_ctx(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref,
         return c;
 }
 
-inline int merit_threads(int na, int N)
-{
-        const int cap = na == 1 ? 128 : 256;
-        int       t = na * N;
-        t = (t + 31) / 32 * 32;
-        return t > cap ? cap : t;
-}
-
 template<class P>
 void launch_kkt(gato_solver* s, const Ctx& c)
 {
-        const int items = c.B * c.N;  // kind 0 has B*N items, kinds 1 and 2 have B*(N-1)
-        k_kkt<P><<<dim3((items + 31) / 32, 3), 32, 0, s->stream>>>(c);
+        enqueue_kkt<P>(c, s->stream);
         s->launches++;
 }
 template<class P>
 void launch_schur(gato_solver* s, const Ctx& c)
 {
-        const int items = c.B * c.N;
-        k_schur<P><<<(items + kSchurWarps - 1) / kSchurWarps, kSchurWarps * 32, s->smem_schur, s->stream>>>(c);
+        enqueue_schur<P>(c, s->smem_schur, s->stream);
         s->launches++;
 }
 template<class P>
 void launch_pcg(gato_solver* s, const Ctx& c)
 {
-        k_pcg<P><<<c.B, s->pcg_threads, s->smem_pcg, s->stream>>>(c);
+        enqueue_pcg<P>(c, s->pcg_rpt, s->pcg_threads, s->smem_pcg, s->stream);
         s->launches++;
 }
 template<class P, int NA>
 void launch_merit(gato_solver* s, const Ctx& c)
 {
-        k_merit_ls<P, NA><<<c.B, merit_threads(NA, c.N), sizeof(float) * (NA * c.N + NA), s->stream>>>(c);
+        enqueue_merit<P>(c, NA, s->stream);
         s->launches++;
 }
 
@@ -493,11 +483,10 @@ int gato_sim_forward(gato_solver* s, float* d_xkp1, const float* d_xk, const flo
 {
         if (!s || !d_xkp1 || !d_xk || !d_uk) return GATO_ERR_ARG;
         if (check_dev(s)) return GATO_ERR_CUDA;
-        const int T = 64, G = (s->B + T - 1) / T;
         if (s->plant == GATO_PLANT_IIWA14)
-                k_sim_forward<Iiwa14><<<G, T, 0, s->stream>>>(s->B, d_xkp1, d_xk, d_uk, s->fext.p, dt);
+                enqueue_sim_forward<Iiwa14>(s->B, d_xkp1, d_xk, d_uk, s->fext.p, dt, s->stream);
         else
-                k_sim_forward<Indy7><<<G, T, 0, s->stream>>>(s->B, d_xkp1, d_xk, d_uk, s->fext.p, dt);
+                enqueue_sim_forward<Indy7>(s->B, d_xkp1, d_xk, d_uk, s->fext.p, dt, s->stream);
         s->launches++;
         CUDA_TRY(s, cudaGetLastError());
         return GATO_OK;

@@ -1,0 +1,2 @@
+#define GATO_TU_PLANT Iiwa14
+#include "tu_linalg.cuh"

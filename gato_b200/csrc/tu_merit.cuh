@@ -1,0 +1,28 @@
+// body of the merit / line-search / sim_forward translation units; GATO_TU_PLANT selects the plant
+#include "launchers.h"
+namespace gato {
+namespace {
+inline int merit_threads(int na, int N)
+{
+        const int cap = na == 1 ? 128 : 256;
+        int       t = na * N;
+        t = (t + 31) / 32 * 32;
+        return t > cap ? cap : t;
+}
+}  // namespace
+template<>
+void enqueue_merit<GATO_TU_PLANT>(const Ctx& c, int na, cudaStream_t st)
+{
+        const size_t smem = sizeof(float) * (size_t)(na * c.N + na);
+        if (na == 1)
+                k_merit_ls<GATO_TU_PLANT, 1><<<c.B, merit_threads(1, c.N), smem, st>>>(c);
+        else
+                k_merit_ls<GATO_TU_PLANT, kNumAlphas><<<c.B, merit_threads(kNumAlphas, c.N), smem, st>>>(c);
+}
+template<>
+void enqueue_sim_forward<GATO_TU_PLANT>(int B, float* xkp1, const float* xk, const float* uk, const float* fext, float dt, cudaStream_t st)
+{
+        const int T = 64, G = (B + T - 1) / T;
+        k_sim_forward<GATO_TU_PLANT><<<G, T, 0, st>>>(B, xkp1, xk, uk, fext, dt);
+}
+}  // namespace gato

@@ -34,7 +34,7 @@ def _inputs(cfg, B, N, seed=11):
     return w, xu, fext
 
 
-@pytest.mark.parametrize("plant,N,cfg,B", [("iiwa14", 8, 1, 3), ("iiwa14", 32, 2, 5), ("indy7", 32, 3, 4), ("indy7", 16, 3, 2), ("iiwa14", 16, 2, 33)])
+@pytest.mark.parametrize("plant,N,cfg,B", [("iiwa14", 8, 1, 3), ("iiwa14", 32, 2, 5), ("indy7", 32, 3, 4), ("indy7", 16, 3, 2), ("iiwa14", 16, 2, 33), ("iiwa14", 128, 4, 2), ("indy7", 64, 3, 2)])
 def test_every_stage_bit_exact_vs_oracle(backends, plant, N, cfg, B):
     o, g = backends(plant, N)
     d = o.d
@@ -76,7 +76,7 @@ def test_every_stage_bit_exact_vs_oracle(backends, plant, N, cfg, B):
             assert n_mismatch(lsg[k], lso[k]) == 0, f"line search {k}"
 
 
-@pytest.mark.parametrize("plant,N,cfg,B", [("iiwa14", 8, 1, 1), ("iiwa14", 32, 2, 16), ("indy7", 32, 3, 16), ("iiwa14", 32, 5, 16)])
+@pytest.mark.parametrize("plant,N,cfg,B", [("iiwa14", 8, 1, 1), ("iiwa14", 32, 2, 16), ("indy7", 32, 3, 16), ("iiwa14", 32, 5, 16), ("iiwa14", 128, 4, 4)])
 def test_whole_solve_bit_exact_vs_oracle(backends, plant, N, cfg, B):
     o, g = backends(plant, N)
     w = make_config(cfg, B=B, N=N)
