@@ -9,7 +9,7 @@ size_t schur_smem_bytes<GATO_TU_PLANT>()
 template<>
 void enqueue_schur<GATO_TU_PLANT>(const Ctx& c, size_t smem, cudaStream_t st)
 {
-        const int items = c.B * c.N;
+        const int items = c.B * ((c.N + 1) / 2);  // one warp per pair of knots
         k_schur<GATO_TU_PLANT><<<(items + kSchurWarps - 1) / kSchurWarps, kSchurWarps * 32, smem, st>>>(c);
 }
 template<>
