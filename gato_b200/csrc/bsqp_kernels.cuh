@@ -22,6 +22,9 @@
 
 namespace gato {
 
+#ifndef GATO_KKT_MIN_BLOCKS
+#define GATO_KKT_MIN_BLOCKS 1
+#endif
 #ifndef GATO_MERIT_MIN_BLOCKS
 #define GATO_MERIT_MIN_BLOCKS 2
 #endif
@@ -66,10 +69,13 @@ __device__ __forceinline__ bool stopped_before(const Ctx& c, int upto)
 // kernel at batch 512.)  Results are transposed through shared memory so that HBM/L2 stores are coalesced per knot block.
 // =====================================================================================================
 template<class P>
-__global__ void __launch_bounds__(32) k_kkt(Ctx c)
+__global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
 {
         constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ, ST = 33;
-        constexpr int ROWS = NX * NX + NX + NU * NU + NU + NX;  // kind 0 needs the most rows: Q | q | R | r | c0
+        // staged floats per item: kind 0: Q (its nq x nq block and the lower diagonal; everything else in Q is a structural zero) | q |
+        // R (diagonal) | r | c0;  kind 1: half of A | c;  kind 2: half of A | B  -- the largest.  26 KB per warp keeps 8 warps per SM.
+        constexpr int ROWS = NX * NQ + NX * NU;
+        static_assert(ROWS >= NQ * NQ + NQ + NX + NU + NU + NX, "kind 0 fits");
         if (stopped_before(c, c.it)) return;
         __shared__ float stage[ROWS * ST];
         const int        kind = blockIdx.y;
@@ -103,18 +109,49 @@ __global__ void __launch_bounds__(32) k_kkt(Ctx c)
         if (kind == 0) {
                 float ref3[3];
                 sfor<0, 3>([&](auto ic) { ref3[ic] = c.ref[(size_t)b * 6 * c.N + 6 * k + ic]; });
-                constexpr int rQ = 0, rq = NX * NX, rR = rq + NX, rr = rR + NU * NU, rc0 = rr + NU;
+                constexpr int rQ = 0, rQd = NQ * NQ, rq = rQd + NQ, rR = rq + NX, rr = rR + NU, rc0 = rr + NU;
+                // Q = [[h h^T w + barrier terms, 0], [0, diag]], R = diag (plant cost Hessians, iiwa14_plant.cuh:400-450): only those entries
+                // are staged; the indices are compile-time constants after inlining, so the stores of structural zeros fold away
                 Items<P>::template cost_grad_hess<true>(
-                    xux, ref3, c.cs, [&](int e, float v) { stage[(rQ + e) * ST + lane] = v; }, [&](int e, float v) { stage[(rq + e) * ST + lane] = v; },
-                    [&](int e, float v) { stage[(rR + e) * ST + lane] = v; }, [&](int e, float v) { stage[(rr + e) * ST + lane] = v; });
+                    xux, ref3, c.cs,
+                    [&](int e, float v) {
+                            const int i = e / NX, j = e % NX;
+                            if (i < NQ && j < NQ)
+                                    stage[(rQ + i * NQ + j) * ST + lane] = v;
+                            else if (i == j)
+                                    stage[(rQd + i - NQ) * ST + lane] = v;
+                    },
+                    [&](int e, float v) { stage[(rq + e) * ST + lane] = v; },
+                    [&](int e, float v) {
+                            if (e / NU == e % NU) stage[(rR + e / NU) * ST + lane] = v;
+                    },
+                    [&](int e, float v) { stage[(rr + e) * ST + lane] = v; });
                 if (term && valid) {
                         const float* x0 = c.xu + (size_t)b * traj;
                         sfor<0, NX>([&](auto ic) { stage[(rc0 + ic) * ST + lane] = x0[ic] - c.xs[(size_t)b * NX + ic]; });
                 }
                 __syncwarp();
-                flush(c.Q, rQ, NX * NX, NX * NX, 0, 0, 2);
+                {  // Q and R: expand the staged entries, zeros elsewhere
+                        const int nvalid = min(32, total - item0);
+                        for (int i = 0; i < nvalid; i++) {
+                                const int  it_ = item0 + i, bi = it_ / per, ki = it_ % per;
+                                float*     dQ = c.Q + ((size_t)bi * c.N + ki) * NX * NX;
+                                for (int e = lane; e < NX * NX; e += 32) {
+                                        const int r_ = e / NX, c_ = e % NX;
+                                        float     v = 0.0f;
+                                        if (r_ < NQ && c_ < NQ)
+                                                v = stage[(rQ + r_ * NQ + c_) * ST + i];
+                                        else if (r_ == c_)
+                                                v = stage[(rQd + r_ - NQ) * ST + i];
+                                        dQ[e] = v;
+                                }
+                                if (ki != c.N - 1) {
+                                        float* dR = c.R + ((size_t)bi * c.N + ki) * NU * NU;
+                                        for (int e = lane; e < NU * NU; e += 32) dR[e] = (e / NU == e % NU) ? stage[(rR + e / NU) * ST + i] : 0.0f;
+                                }
+                        }
+                }
                 flush(c.q, rq, NX, NX, 0, 0, 2);
-                flush(c.R, rR, NU * NU, NU * NU, 0, 0, 0);
                 flush(c.r, rr, NU, NU, 0, 0, 0);
                 flush(c.c, rc0, NX, NX, 0, -(c.N - 1), 1);
         } else {
