@@ -5,6 +5,7 @@ when the shared library is missing, and every call fails with the library's erro
 kernel image is available.
 """
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
@@ -39,7 +40,9 @@ _LIB = None
 
 
 def lib_path():
-    return Path(__file__).resolve().parent / "lib" / "libgato_b200.so"
+    """The in-tree shared library; GATO_B200_LIB overrides it (used to A/B kernel build variants on the GPU box)."""
+    override = os.environ.get("GATO_B200_LIB")
+    return Path(override) if override else Path(__file__).resolve().parent / "lib" / "libgato_b200.so"
 
 
 def load():

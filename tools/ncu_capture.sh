@@ -5,7 +5,7 @@ set -u
 TAG=${1:-cur}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu --no-ref-gpu --no-e2e"
-for K in k_pcg k_schur k_kkt k_merit_ls; do
+for K in ${KERNELS:-k_pcg k_schur k_kkt k_merit_ls}; do
     # skip the first warm-up step's launches of this kernel, capture one launch
     ncu --set full --clock-control none --import-source on -k regex:"^${K}" -s 5 -c 1 -f -o /tmp/prof_${K} $CMD > /tmp/ncu_${K}.log 2>&1
     ncu -i /tmp/prof_${K}.ncu-rep --page raw --csv > gpurun_out/${TAG}_${K}_raw.csv 2>/dev/null
