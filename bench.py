@@ -34,6 +34,14 @@ FLOP_PER_SQP_ITER = 7.06e6 + 0.08e6 * 51
 FLOP_MERIT_EXTRA = 0.88e6
 FLOP_PER_SOLVE = 4 * FLOP_PER_SQP_ITER + FLOP_MERIT_EXTRA
 BYTES_PER_SOLVE = 10024  # compulsory HBM I/O per solve (xu, ref, x_s, f_ext, lambda in; xu, lambda, stats out)
+# algorithmic bytes ONE k_pcg launch moves per solve (iiwa14, N=32): rows of S and P^-1, gamma, lambda in/out, and
+# for the primal step A, B, Q^-1, R^-1, q, r (read-modify-write) and dz
+_N, _NX, _NU = 32, 14, 7
+PCG_FLOATS_PER_SOLVE = (2 * _N * 3 * _NX * _NX + 3 * (_N + 2) * _NX + (_N - 1) * _NX * _NX + (_N - 1) * _NX * _NU + _N * _NX * _NX + (_N - 1) * _NU * _NU
+                        + 2 * _N * _NX + 2 * (_N - 1) * _NU + (_N * (_NX + _NU) - _NU))
+PCG_BYTES_PER_SOLVE = 4 * PCG_FLOATS_PER_SOLVE
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_pcg launch at batch 512 (ncu --set full, cold caches; profiles/r01_v7_k_pcg_raw.csv)
+PCG_NCU_TRAFFIC_BYTES_B512 = 115.111936e6 + 6.153984e6
 FP32_NOMINAL_TFLOPS = 74.4  # 148 SM x 128 lanes x 2 x 1.965 GHz (no fp32 number in MEASURED_PEAKS.json)
 
 
@@ -120,6 +128,17 @@ def reference_gpu_row(w):
         return {"unavailable": str(e)[:200]}
 
 
+def roofline_pcg(kernels, B, hbm_peak, peak_source):
+    k = kernels.get("k_pcg")
+    if not k:
+        return {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None, "kernel": "k_pcg"}
+    gbs = B * PCG_BYTES_PER_SOLVE / (k["us_per_launch"] * 1e-6) / 1e9
+    return {"bound": "hbm", "kernel": "k_pcg", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+            "traffic": PCG_NCU_TRAFFIC_BYTES_B512 * B / 512 if B == 512 else None, "algorithmic_bytes_per_launch": B * PCG_BYTES_PER_SOLVE,
+            "us_per_launch": k["us_per_launch"], "share_of_step": k["share_of_step"], "peak_source": peak_source,
+            "limiter": "issue/latency (4 CTA-wide barriers and two dependent reduction trees per PCG iteration), not HBM"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -200,6 +219,24 @@ def main():
     value = B * world * args.steps / (total_ms * 1e-3)
     ms_per_step = total_ms / args.steps
 
+    # ---- per-kernel durations: a few extra steps with the library's event-per-launch instrumentation (not part of the timed region) ----
+    kernels = {}
+    if rank == 0:
+        solver.set_kernel_timing(True)
+        acc = {}
+        reps = 5
+        for _ in range(reps):
+            one_step(False)
+            for k, (ms, n) in solver.kernel_times().items():
+                a = acc.setdefault(k, [0.0, 0])
+                a[0] += ms
+                a[1] += n
+        solver.set_kernel_timing(False)
+        tot_k = sum(a[0] for a in acc.values())
+        for k, (ms, n) in acc.items():
+            if n:
+                kernels[k] = {"us_per_launch": 1e3 * ms / n, "launches_per_step": n // reps, "share_of_step": ms / tot_k}
+
     # ---- e2e: host buffers, pinned, H2D + D2H inside the window ----
     e2e = None
     if not args.no_e2e:
@@ -262,20 +299,22 @@ def main():
         "latency_ms_p50": float(np.median(step_ms)),
         "gpu_launches": int(launches),
         "clocks": clocks_summary(samples),
-        # the path is FP32-FMA / latency bound with ~10 KB of compulsory HBM traffic per solve: the HBM roof
-        # is reported because the contract asks for it; the FP32 fraction is the informative one
-        "roofline": {"bound": "hbm", "achieved": per_gpu_solves_per_s * BYTES_PER_SOLVE / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": per_gpu_solves_per_s * BYTES_PER_SOLVE / 1e9 / hbm_peak, "traffic": None,
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s", "scope": "whole solve (all launches of one step)"},
-        "roofline_fp32": {"achieved": per_gpu_solves_per_s * FLOP_PER_SOLVE / 1e12, "peak": FP32_NOMINAL_TFLOPS, "unit": "TFLOP/s",
+        # roofline of the dominant kernel (k_pcg, about half of the step): algorithmic bytes of one launch / its CUDA-event duration against
+        # the measured HBM copy peak.  The kernel is issue/latency bound, not HBM bound: the whole path has ~10 KB of
+        # compulsory HBM traffic and ~45 Mflop per solve, so the FP32 fraction of the whole step is reported next to it.
+        "roofline": roofline_pcg(kernels, B, hbm_peak, "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"),
+        "roofline_fp32": {"scope": "whole step", "achieved": per_gpu_solves_per_s * FLOP_PER_SOLVE / 1e12, "peak": FP32_NOMINAL_TFLOPS, "unit": "TFLOP/s",
                           "frac": per_gpu_solves_per_s * FLOP_PER_SOLVE / 1e12 / FP32_NOMINAL_TFLOPS, "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"},
+        "roofline_hbm_whole_step": {"achieved": per_gpu_solves_per_s * BYTES_PER_SOLVE / 1e9, "unit": "GB/s", "frac": per_gpu_solves_per_s * BYTES_PER_SOLVE / 1e9 / hbm_peak,
+                                    "note": "compulsory I/O only (10 024 B per solve)"},
+        "kernels": kernels,
     }
     if e2e:
         line["e2e"] = e2e
     if not args.no_ref_gpu and world == 1:
         line["reference_gpu"] = reference_gpu_row(make_config("bench", B=B))
     if not args.no_cpu and world == 1:
-        n = 256
+        n = 1024
         rate, cores, times = cpu_oracle_rate(n, 3)
         line["cpu_baseline"] = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
                                 "sample": f"{n} solves of the same workload, median of 3 passes ({sum(times):.1f} s of wall time on {cores} threads)"}

@@ -68,6 +68,11 @@ struct gato_solver {
         cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
         std::string  err;
         long         launches = 0;
+        // optional per-kernel timing: events e[0] K0 e[1] K1 ... on the stream; tick_class[i] = class of the kernel after e[i]
+        bool                     timing = false;
+        std::vector<cudaEvent_t> tick_ev;
+        std::vector<int>         tick_class;
+        size_t                   n_ticks = 0;
         int          max_it;
         // device state
         DevArr<float>    Q, R, q, r, A, Bm, c, Qinv, Rinv, S, Pinv, gamma, lambda, dz;
@@ -148,27 +153,44 @@ Ctx make_ctx(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref,
         return c;
 }
 
+// timing: record an event before a kernel of class `cls` (cls < 0: closing event)
+void tick(gato_solver* s, int cls)
+{
+        if (!s->timing) return;
+        if (s->n_ticks == s->tick_ev.size()) {
+                cudaEvent_t e;
+                if (cudaEventCreate(&e) != cudaSuccess) return;
+                s->tick_ev.push_back(e);
+                s->tick_class.push_back(-1);
+        }
+        s->tick_class[s->n_ticks] = cls;
+        cudaEventRecord(s->tick_ev[s->n_ticks++], s->stream);
+}
 template<class P>
 void launch_kkt(gato_solver* s, const Ctx& c)
 {
+        tick(s, 0);
         enqueue_kkt<P>(c, s->stream);
         s->launches++;
 }
 template<class P>
 void launch_schur(gato_solver* s, const Ctx& c)
 {
+        tick(s, 1);
         enqueue_schur<P>(c, s->smem_schur, s->stream);
         s->launches++;
 }
 template<class P>
 void launch_pcg(gato_solver* s, const Ctx& c)
 {
+        tick(s, 2);
         enqueue_pcg<P>(c, s->pcg_rpt, s->pcg_threads, s->smem_pcg, s->stream);
         s->launches++;
 }
 template<class P, int NA>
 void launch_merit(gato_solver* s, const Ctx& c)
 {
+        tick(s, NA == 1 ? 4 : 3);
         enqueue_merit<P>(c, NA, s->stream);
         s->launches++;
 }
@@ -179,12 +201,14 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
 {
         const int B = s->B;
         Ctx       c = make_ctx(s, d_xu, d_xs, d_ref, dt);
+        s->n_ticks = 0;
         CUDA_TRY(s, cudaMemsetAsync(s->conv.p, 0, sizeof(int) * B, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->num_solved.p, 0, sizeof(unsigned) * s->max_it, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->pcg_log.p, 0, sizeof(int) * (size_t)s->max_it * B, s->stream));
         // initial merit (dz = 0, alpha = 1)  bsqp.cuh:116-118
         c.flags = F_MERIT | F_ZERO_DZ;
         launch_merit<P, 1>(s, c);
+        tick(s, -1);
         CUDA_TRY(s, cudaMemcpyAsync(s->merit0.p, s->merit_cur.p, sizeof(float) * B, cudaMemcpyDeviceToDevice, s->stream));
         for (int it = 0; it < s->max_it; it++) {
                 c.it = it;
@@ -199,6 +223,7 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
         // final merit on the updated trajectory  bsqp.cuh:180-182
         c.flags = F_MERIT | F_ZERO_DZ;
         launch_merit<P, 1>(s, c);
+        tick(s, -1);
         CUDA_TRY(s, cudaGetLastError());
         // results -> pinned host buffers
         CUDA_TRY(s, cudaMemcpyAsync(s->h_num_solved, s->num_solved.p, sizeof(unsigned) * s->max_it, cudaMemcpyDeviceToHost, s->stream));
@@ -267,6 +292,34 @@ int gato_dims(int plant, int N, int* nx, int* nu, int* traj)
 
 const char* gato_last_error(const gato_solver* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
 long        gato_kernel_launches(const gato_solver* s) { return s ? s->launches : 0; }
+
+int gato_set_kernel_timing(gato_solver* s, int enable)
+{
+        if (!s) return GATO_ERR_ARG;
+        s->timing = enable != 0;
+        s->n_ticks = 0;
+        return GATO_OK;
+}
+
+int gato_get_kernel_times(gato_solver* s, float* total_ms, int* launches)
+{
+        if (!s || !total_ms || !launches) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        if (s->pending) {
+                s->err = "gato_get_kernel_times: a solve is still pending (call gato_solve_wait first)";
+                return GATO_ERR_ARG;
+        }
+        for (int i = 0; i < GATO_NUM_KERNEL_CLASSES; i++) total_ms[i] = 0.0f, launches[i] = 0;
+        for (size_t i = 0; i + 1 < s->n_ticks; i++) {
+                const int cls = s->tick_class[i];
+                if (cls < 0) continue;
+                float ms = 0.0f;
+                CUDA_TRY(s, cudaEventElapsedTime(&ms, s->tick_ev[i], s->tick_ev[i + 1]));
+                total_ms[cls] += ms;
+                launches[cls]++;
+        }
+        return GATO_OK;
+}
 
 int gato_create(gato_solver** out, int plant, int N, int B, int device, void* stream, const gato_params* prm)
 {
@@ -353,6 +406,7 @@ void gato_destroy(gato_solver* s)
         s->conv.release(), s->pcg_log.release(), s->num_solved.release();
         for (void* p : {(void*)s->h_pcg_log, (void*)s->h_conv, (void*)s->h_num_solved, (void*)s->h_ls_merit, (void*)s->h_ls_step, (void*)s->h_final, (void*)s->h_initial})
                 if (p) cudaFreeHost(p);
+        for (cudaEvent_t e : s->tick_ev) cudaEventDestroy(e);
         if (s->ev0) cudaEventDestroy(s->ev0);
         if (s->ev1) cudaEventDestroy(s->ev1);
         if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);

@@ -73,6 +73,8 @@ def load():
     lib.gato_dims.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.gato_kernel_launches.argtypes = [vp]
     lib.gato_kernel_launches.restype = C.c_long
+    lib.gato_set_kernel_timing.argtypes = [vp, C.c_int]
+    lib.gato_get_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.gato_get_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lead = [C.c_int, C.c_int, C.c_int]
     lib.gato_stage_kkt.argtypes = lead + [f32p] * 4 + [C.c_float, f32p] + [f32p] * 7
@@ -185,6 +187,18 @@ class Solver:
 
     def kernel_launches(self):
         return int(self.lib.gato_kernel_launches(self.h))
+
+    KERNEL_CLASSES = ("k_kkt", "k_schur", "k_pcg", "k_merit_ls<8>", "k_merit_ls<1>")
+
+    def set_kernel_timing(self, enable=True):
+        self._check(self.lib.gato_set_kernel_timing(self.h, int(bool(enable))), "set_kernel_timing")
+
+    def kernel_times(self):
+        """{kernel: (total ms, launches)} of the last completed solve (needs set_kernel_timing(True) before it)."""
+        ms = (C.c_float * 5)()
+        n = (C.c_int * 5)()
+        self._check(self.lib.gato_get_kernel_times(self.h, ms, n), "get_kernel_times")
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
 
 class GatoBackend:

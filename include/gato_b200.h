@@ -91,6 +91,12 @@ int gato_get_merits(gato_solver* s, float* h_final /*[B] or NULL*/, float* h_ini
 int  gato_dims(int plant, int knot_points, int* nx, int* nu, int* traj_size);
 long gato_kernel_launches(const gato_solver* s); /* kernels launched by this solver so far */
 int  gato_get_device_pointers(gato_solver* s, float** d_xu, float** d_x_s, float** d_ref); /* solver-owned staging buffers used by *_host calls */
+/* Per-kernel device timing (measurement aid, off by default): when enabled, every kernel launch of a solve is bracketed by CUDA
+ * events on the solver's stream.  gato_get_kernel_times returns, for the LAST completed solve, the summed duration and the number
+ * of launches per kernel class: 0 k_kkt, 1 k_schur, 2 k_pcg, 3 k_merit_ls<8> (merit + line search), 4 k_merit_ls<1>. */
+#define GATO_NUM_KERNEL_CLASSES 5
+int gato_set_kernel_timing(gato_solver* s, int enable);
+int gato_get_kernel_times(gato_solver* s, float* total_ms /* [5] */, int* launches /* [5] */);
 
 /* Stage-level entry points (host buffers; used by the parity tests, same layouts as the reference kernels'
  * global buffers — setup_kkt.cuh:15, schur_linsys.cuh:14/214/316, pcg.cuh:14, merit.cuh:17, line_search.cuh:13). */
