@@ -293,6 +293,25 @@ int gato_dims(int plant, int N, int* nx, int* nu, int* traj)
 const char* gato_last_error(const gato_solver* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
 long        gato_kernel_launches(const gato_solver* s) { return s ? s->launches : 0; }
 
+int gato_get_launch_times(gato_solver* s, int* kernel_class, float* ms, int cap)
+{
+        if (!s || !kernel_class || !ms || cap < 0) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        if (s->pending) {
+                s->err = "gato_get_launch_times: a solve is still pending (call gato_solve_wait first)";
+                return GATO_ERR_ARG;
+        }
+        int n = 0;
+        for (size_t i = 0; i + 1 < s->n_ticks && n < cap; i++) {
+                if (s->tick_class[i] < 0) continue;
+                float t = 0.0f;
+                CUDA_TRY(s, cudaEventElapsedTime(&t, s->tick_ev[i], s->tick_ev[i + 1]));
+                kernel_class[n] = s->tick_class[i];
+                ms[n++] = t;
+        }
+        return n;
+}
+
 int gato_set_kernel_timing(gato_solver* s, int enable)
 {
         if (!s) return GATO_ERR_ARG;

@@ -75,6 +75,7 @@ def load():
     lib.gato_kernel_launches.restype = C.c_long
     lib.gato_set_kernel_timing.argtypes = [vp, C.c_int]
     lib.gato_get_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    lib.gato_get_launch_times.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]
     lib.gato_get_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lead = [C.c_int, C.c_int, C.c_int]
     lib.gato_stage_kkt.argtypes = lead + [f32p] * 4 + [C.c_float, f32p] + [f32p] * 7
@@ -192,6 +193,15 @@ class Solver:
 
     def set_kernel_timing(self, enable=True):
         self._check(self.lib.gato_set_kernel_timing(self.h, int(bool(enable))), "set_kernel_timing")
+
+    def launch_times(self, cap=256):
+        """[(kernel, ms), ...] of the last completed solve, in launch order."""
+        cls = (C.c_int * cap)()
+        ms = (C.c_float * cap)()
+        n = self.lib.gato_get_launch_times(self.h, cls, ms, cap)
+        if n < 0:
+            self._check(n, "get_launch_times")
+        return [(self.KERNEL_CLASSES[cls[i]], float(ms[i])) for i in range(n)]
 
     def kernel_times(self):
         """{kernel: (total ms, launches)} of the last completed solve (needs set_kernel_timing(True) before it)."""

@@ -97,6 +97,8 @@ int  gato_get_device_pointers(gato_solver* s, float** d_xu, float** d_x_s, float
 #define GATO_NUM_KERNEL_CLASSES 5
 int gato_set_kernel_timing(gato_solver* s, int enable);
 int gato_get_kernel_times(gato_solver* s, float* total_ms /* [5] */, int* launches /* [5] */);
+/* every launch of the last completed solve in launch order: class id and duration; returns the number of launches written (<= cap) or < 0 */
+int gato_get_launch_times(gato_solver* s, int* kernel_class, float* ms, int cap);
 
 /* Stage-level entry points (host buffers; used by the parity tests, same layouts as the reference kernels'
  * global buffers — setup_kkt.cuh:15, schur_linsys.cuh:14/214/316, pcg.cuh:14, merit.cuh:17, line_search.cuh:13). */
