@@ -68,6 +68,15 @@ struct gato_solver {
         cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
         std::string  err;
         long         launches = 0;
+        // closed-loop MPC step state (allocated on first use)
+        DevArr<float>  mpc_xu, mpc_xs, mpc_ref, mpc_off, mpc_in, mpc_xnext;
+        DevArr<double> mpc_err;
+        DevArr<int>    mpc_best;
+        bool           mpc_has_off = false;
+        float*         h_mpc_in = nullptr;    // pinned: x_curr | ref window | x_last | u_last
+        float*         h_mpc_best = nullptr;  // pinned: selected trajectory
+        double*        h_mpc_err = nullptr;   // pinned: [B] errors
+        int*           h_mpc_id = nullptr;    // pinned: best id
         // optional per-kernel timing: events e[0] K0 e[1] K1 ... on the stream; tick_class[i] = class of the kernel after e[i]
         bool                     timing = false;
         std::vector<cudaEvent_t> tick_ev;
@@ -425,6 +434,10 @@ void gato_destroy(gato_solver* s)
         s->conv.release(), s->pcg_log.release(), s->num_solved.release();
         for (void* p : {(void*)s->h_pcg_log, (void*)s->h_conv, (void*)s->h_num_solved, (void*)s->h_ls_merit, (void*)s->h_ls_step, (void*)s->h_final, (void*)s->h_initial})
                 if (p) cudaFreeHost(p);
+        for (auto* a : {&s->mpc_xu, &s->mpc_xs, &s->mpc_ref, &s->mpc_off, &s->mpc_in, &s->mpc_xnext}) a->release();
+        s->mpc_err.release(), s->mpc_best.release();
+        for (void* p : {(void*)s->h_mpc_in, (void*)s->h_mpc_best, (void*)s->h_mpc_err, (void*)s->h_mpc_id})
+                if (p) cudaFreeHost(p);
         for (cudaEvent_t e : s->tick_ev) cudaEventDestroy(e);
         if (s->ev0) cudaEventDestroy(s->ev0);
         if (s->ev1) cudaEventDestroy(s->ev1);
@@ -576,6 +589,206 @@ int gato_sim_forward_host(gato_solver* s, float* h_xkp1, const float* h_xk, cons
         if (rc) return rc;
         CUDA_TRY(s, cudaMemcpyAsync(h_xkp1, s->st_xkp1.p, sizeof(float) * (size_t)s->B * s->d.nx, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        return GATO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// closed-loop MPC step (python/bsqp/mpc_controller.py:233-253, 294-309)
+// ------------------------------------------------------------------------------------------------
+namespace {
+// in = x_curr[nx] | ref[6N] | x_last[nx] | u_last[nu]
+__global__ void k_mpc_prepare(int B, int nx, int N, int traj, const float* __restrict__ in, const float* __restrict__ off, float* xs, float* ref, float* xu)
+{
+        const int b = blockIdx.x;
+        for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+                float v = in[i];
+                if (off) v = v + off[(size_t)b * nx + i];
+                xs[(size_t)b * nx + i] = v;
+                xu[(size_t)b * traj + i] = v;
+        }
+        for (int i = threadIdx.x; i < 6 * N; i += blockDim.x) ref[(size_t)b * 6 * N + i] = in[nx + i];
+}
+// err[b] = sqrt(sum_i (double(xnext[b][i]) - double(x_curr[i]))^2) with numpy's pairwise order for a contiguous row of n < 128 doubles
+// (eight running sums over the first 8*(n/8) entries, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail in order);
+// best = first index of the minimum (np.argmin).  One CTA.
+__global__ void k_mpc_score(int B, int nx, const float* __restrict__ xnext, const float* __restrict__ in, double* err, int* best)
+{
+        __shared__ double s_val[256];
+        __shared__ int    s_idx[256];
+        double            bv = 0.0;
+        int               bi = -1;
+        for (int b = threadIdx.x; b < B; b += blockDim.x) {
+                const float* x = xnext + (size_t)b * nx;
+                double       res;
+                auto         sq = [&](int i) {
+                        const double d = (double)x[i] - (double)in[i];
+                        return d * d;
+                };
+                if (nx < 8) {
+                        res = 0.0;
+                        for (int i = 0; i < nx; i++) res += sq(i);
+                } else {
+                        double r[8];
+                        for (int j = 0; j < 8; j++) r[j] = sq(j);
+                        int i = 8;
+                        for (; i < nx - (nx % 8); i += 8)
+                                for (int j = 0; j < 8; j++) r[j] += sq(i + j);
+                        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+                        for (; i < nx; i++) res += sq(i);
+                }
+                const double e = sqrt(res);
+                err[b] = e;
+                if (bi < 0 || e < bv) bv = e, bi = b;  // ascending b per thread: strict < keeps the first minimum
+        }
+        s_val[threadIdx.x] = bv;
+        s_idx[threadIdx.x] = bi;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+                double v = 0.0;
+                int    id = -1;
+                for (int t = 0; t < (int)blockDim.x; t++) {
+                        if (s_idx[t] < 0) continue;
+                        if (id < 0 || s_val[t] < v || (s_val[t] == v && s_idx[t] < id)) v = s_val[t], id = s_idx[t];
+                }
+                // NaN errors: np.argmin returns the first NaN; keep it simple and deterministic: NaNs never win, id stays >= 0 if any finite
+                best[0] = id < 0 ? 0 : id;
+        }
+}
+__global__ void k_mpc_adopt(int B, int traj, float* xu, const int* best, float* best_out)
+{
+        const int    b = blockIdx.x, src = best[0];
+        const float* s = xu + (size_t)src * traj;
+        if (b == B) {  // extra block: export the winner
+                for (int i = threadIdx.x; i < traj; i += blockDim.x) best_out[i] = s[i];
+                return;
+        }
+        if (b == src) return;
+        float* d = xu + (size_t)b * traj;
+        for (int i = threadIdx.x; i < traj; i += blockDim.x) d[i] = s[i];
+}
+
+int mpc_ensure(gato_solver* s)
+{
+        if (s->mpc_xu.p) return GATO_OK;
+        const Dims&  d = s->d;
+        const size_t B = (size_t)s->B;
+        CUDA_TRY(s, s->mpc_xu.alloc(B * d.traj));
+        CUDA_TRY(s, s->mpc_xs.alloc(B * d.nx));
+        CUDA_TRY(s, s->mpc_ref.alloc(B * 6 * d.N));
+        CUDA_TRY(s, s->mpc_off.alloc(B * d.nx));
+        CUDA_TRY(s, s->mpc_in.alloc(2 * d.nx + 6 * d.N + d.nu));
+        CUDA_TRY(s, s->mpc_xnext.alloc(B * d.nx + d.traj));  // x_next batch, then the exported winner
+        CUDA_TRY(s, s->mpc_err.alloc(B));
+        CUDA_TRY(s, s->mpc_best.alloc(1));
+        CUDA_TRY(s, cudaMallocHost((void**)&s->h_mpc_in, sizeof(float) * (2 * d.nx + 6 * d.N + d.nu)));
+        CUDA_TRY(s, cudaMallocHost((void**)&s->h_mpc_best, sizeof(float) * d.traj));
+        CUDA_TRY(s, cudaMallocHost((void**)&s->h_mpc_err, sizeof(double) * B));
+        CUDA_TRY(s, cudaMallocHost((void**)&s->h_mpc_id, sizeof(int)));
+        return GATO_OK;
+}
+}  // namespace
+
+int gato_mpc_set_warm_start(gato_solver* s, const float* h_xu, int per_solve)
+{
+        if (!s || !h_xu) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        if (int rc = mpc_ensure(s)) return rc;
+        const size_t traj = s->d.traj;
+        if (per_solve) {
+                CUDA_TRY(s, cudaMemcpyAsync(s->mpc_xu.p, h_xu, sizeof(float) * s->B * traj, cudaMemcpyHostToDevice, s->stream));
+        } else {
+                for (int b = 0; b < s->B; b++) CUDA_TRY(s, cudaMemcpyAsync(s->mpc_xu.p + b * traj, h_xu, sizeof(float) * traj, cudaMemcpyHostToDevice, s->stream));
+        }
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        return GATO_OK;
+}
+
+int gato_mpc_set_state_offsets(gato_solver* s, const float* h_x_offset)
+{
+        if (!s) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        if (int rc = mpc_ensure(s)) return rc;
+        s->mpc_has_off = h_x_offset != nullptr;
+        if (h_x_offset) {
+                CUDA_TRY(s, cudaMemcpyAsync(s->mpc_off.p, h_x_offset, sizeof(float) * (size_t)s->B * s->d.nx, cudaMemcpyHostToDevice, s->stream));
+                CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        }
+        return GATO_OK;
+}
+
+int gato_mpc_get_warm_start(gato_solver* s, float* h_xu)
+{
+        if (!s || !h_xu) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        if (!s->mpc_xu.p) {
+                s->err = "gato_mpc_get_warm_start: no warm start has been set";
+                return GATO_ERR_ARG;
+        }
+        CUDA_TRY(s, cudaMemcpyAsync(h_xu, s->mpc_xu.p, sizeof(float) * (size_t)s->B * s->d.traj, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        return GATO_OK;
+}
+
+int gato_mpc_step(gato_solver* s, const float* h_x_curr, const float* h_ref_window, const float* h_x_last, const float* h_u_last, float sim_dt, float timestep, int flags,
+                  gato_mpc_out* out, gato_stats* st)
+{
+        if (!s || !h_x_curr || !h_ref_window || !out || ((h_x_last == nullptr) != (h_u_last == nullptr))) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        if (!s->mpc_xu.p) {
+                s->err = "gato_mpc_step: call gato_mpc_set_warm_start first";
+                return GATO_ERR_ARG;
+        }
+        const Dims& d = s->d;
+        const int   B = s->B, nin = 2 * d.nx + 6 * d.N + d.nu;
+        const bool  score = h_x_last != nullptr;
+        s->t_start = std::chrono::high_resolution_clock::now();
+        memcpy(s->h_mpc_in, h_x_curr, sizeof(float) * d.nx);
+        memcpy(s->h_mpc_in + d.nx, h_ref_window, sizeof(float) * 6 * d.N);
+        if (score) {
+                memcpy(s->h_mpc_in + d.nx + 6 * d.N, h_x_last, sizeof(float) * d.nx);
+                memcpy(s->h_mpc_in + 2 * d.nx + 6 * d.N, h_u_last, sizeof(float) * d.nu);
+        }
+        CUDA_TRY(s, cudaMemcpyAsync(s->mpc_in.p, s->h_mpc_in, sizeof(float) * nin, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaEventRecord(s->ev0, s->stream));
+        k_mpc_prepare<<<B, 64, 0, s->stream>>>(B, d.nx, d.N, d.traj, s->mpc_in.p, s->mpc_has_off ? s->mpc_off.p : nullptr, s->mpc_xs.p, s->mpc_ref.p, s->mpc_xu.p);
+        s->launches++;
+        if (flags & GATO_MPC_RESET_RHO) {
+                CUDA_TRY(s, cudaMemcpyAsync(s->rho.p, s->h_rho_init.data(), sizeof(float) * B, cudaMemcpyHostToDevice, s->stream));
+                CUDA_TRY(s, cudaMemcpyAsync(s->drho.p, s->h_drho_init.data(), sizeof(float) * B, cudaMemcpyHostToDevice, s->stream));
+        }
+        if (int rc = dispatch_enqueue(s, s->mpc_xu.p, s->mpc_xs.p, s->mpc_ref.p, timestep)) return rc;
+        float* d_best_out = s->mpc_xnext.p + (size_t)B * d.nx;
+        if (score) {
+                const float* d_xl = s->mpc_in.p + d.nx + 6 * d.N;
+                if (s->plant == GATO_PLANT_IIWA14)
+                        enqueue_sim_forward<Iiwa14>(B, s->mpc_xnext.p, d_xl, d_xl + d.nx, s->fext.p, sim_dt, s->stream);
+                else
+                        enqueue_sim_forward<Indy7>(B, s->mpc_xnext.p, d_xl, d_xl + d.nx, s->fext.p, sim_dt, s->stream);
+                k_mpc_score<<<1, 256, 0, s->stream>>>(B, d.nx, s->mpc_xnext.p, s->mpc_in.p, s->mpc_err.p, s->mpc_best.p);
+                s->launches += 2;
+        } else {
+                CUDA_TRY(s, cudaMemsetAsync(s->mpc_best.p, 0, sizeof(int), s->stream));
+                CUDA_TRY(s, cudaMemsetAsync(s->mpc_err.p, 0, sizeof(double) * B, s->stream));
+        }
+        k_mpc_adopt<<<B + 1, 128, 0, s->stream>>>(B, d.traj, s->mpc_xu.p, s->mpc_best.p, d_best_out);
+        s->launches++;
+        CUDA_TRY(s, cudaEventRecord(s->ev1, s->stream));
+        CUDA_TRY(s, cudaGetLastError());
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_mpc_best, d_best_out, sizeof(float) * d.traj, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_mpc_err, s->mpc_err.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_mpc_id, s->mpc_best.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        fill_stats(s, st);
+        if (st) {
+                st->solve_time_us = std::chrono::duration<double, std::micro>(std::chrono::high_resolution_clock::now() - s->t_start).count();
+                float ms = 0;
+                CUDA_TRY(s, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+                st->device_time_ms = ms;
+        }
+        out->best_id = *s->h_mpc_id;
+        out->best_error = s->h_mpc_err[out->best_id];
+        out->errors = s->h_mpc_err;
+        out->xu_best = s->h_mpc_best;
         return GATO_OK;
 }
 

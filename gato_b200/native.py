@@ -32,6 +32,10 @@ class GatoStats(C.Structure):
                 ("final_merit", C.POINTER(C.c_float)), ("initial_merit", C.POINTER(C.c_float))]
 
 
+class GatoMpcOut(C.Structure):
+    _fields_ = [("best_id", C.c_int32), ("best_error", C.c_double), ("errors", C.POINTER(C.c_double)), ("xu_best", C.POINTER(C.c_float))]
+
+
 class GatoError(RuntimeError):
     pass
 
@@ -73,6 +77,10 @@ def load():
     lib.gato_dims.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.gato_kernel_launches.argtypes = [vp]
     lib.gato_kernel_launches.restype = C.c_long
+    lib.gato_mpc_set_warm_start.argtypes = [vp, f32p, C.c_int]
+    lib.gato_mpc_set_state_offsets.argtypes = [vp, C.c_void_p]
+    lib.gato_mpc_get_warm_start.argtypes = [vp, f32p]
+    lib.gato_mpc_step.argtypes = [vp, f32p, f32p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.POINTER(GatoMpcOut), C.POINTER(GatoStats)]
     lib.gato_set_kernel_timing.argtypes = [vp, C.c_int]
     lib.gato_get_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.gato_get_launch_times.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]
@@ -185,6 +193,41 @@ class Solver:
         out = np.zeros((self.B, self.d["nx"]), np.float32)
         self._check(self.lib.gato_sim_forward_host(self.h, out.reshape(-1), _f(xk), _f(uk), float(dt)), "gato_sim_forward_host")
         return out
+
+    # ---- closed-loop MPC step on the device (include/gato_b200.h: gato_mpc_*) ----
+    def mpc_set_warm_start(self, xu):
+        xu = _f(xu)
+        per_solve = xu.size == self.B * self.d["traj"] and self.B > 1
+        assert per_solve or xu.size == self.d["traj"]
+        self._check(self.lib.gato_mpc_set_warm_start(self.h, xu.reshape(-1), int(per_solve)), "gato_mpc_set_warm_start")
+
+    def mpc_set_state_offsets(self, off):
+        if off is None:
+            self._check(self.lib.gato_mpc_set_state_offsets(self.h, None), "gato_mpc_set_state_offsets")
+        else:
+            off = _f(off).reshape(self.B, self.d["nx"])
+            self._check(self.lib.gato_mpc_set_state_offsets(self.h, off.ctypes.data_as(C.c_void_p)), "gato_mpc_set_state_offsets")
+
+    def mpc_get_warm_start(self):
+        out = np.zeros((self.B, self.d["traj"]), np.float32)
+        self._check(self.lib.gato_mpc_get_warm_start(self.h, out.reshape(-1)), "gato_mpc_get_warm_start")
+        return out
+
+    def mpc_step(self, x_curr, ref_window, x_last=None, u_last=None, sim_dt=0.0, dt=0.01, reset_rho=True):
+        """One control step: broadcast (x_curr, ref_window), solve, score the hypotheses with sim_forward, adopt the best trajectory.
+        Returns the statistics dictionary plus best_id, errors[B] (float64) and XU_best[traj]."""
+        x_curr, ref_window = _f(x_curr), _f(ref_window)
+        xl = ul = None
+        if x_last is not None:
+            xl_a, ul_a = _f(x_last), _f(u_last)
+            xl, ul = xl_a.ctypes.data_as(C.c_void_p), ul_a.ctypes.data_as(C.c_void_p)
+        out, st = GatoMpcOut(), GatoStats()
+        self._check(self.lib.gato_mpc_step(self.h, x_curr, ref_window, xl, ul, float(sim_dt), float(dt), 1 if reset_rho else 0, C.byref(out), C.byref(st)), "gato_mpc_step")
+        res = self._stats(st)
+        res["best_id"] = int(out.best_id)
+        res["errors"] = np.ctypeslib.as_array(out.errors, shape=(self.B,)).copy()
+        res["XU_best"] = np.ctypeslib.as_array(out.xu_best, shape=(self.d["traj"],)).copy()
+        return res
 
     def kernel_launches(self):
         return int(self.lib.gato_kernel_launches(self.h))

@@ -87,6 +87,27 @@ int gato_sim_forward(gato_solver* s, float* d_xkp1 /*[B][nx]*/, const float* d_x
 int gato_sim_forward_host(gato_solver* s, float* h_xkp1, const float* h_xk, const float* h_uk, float dt);
 int gato_get_merits(gato_solver* s, float* h_final /*[B] or NULL*/, float* h_initial /*[B] or NULL*/);
 
+/* Closed-loop MPC step on the device: what python/bsqp/mpc_controller.py:233-253,294-309 does per control
+ * step through four host round trips, as ONE stream of device work with one synchronisation:
+ *   x_s[b] = x_curr (+ x_offset[b] if set), ref[b] = ref_window, XU[b][0:nx] = x_s[b]          (mpc_controller.py:238-242)
+ *   reset_rho (optional, :245), solve (:248),
+ *   x_next[b] = sim_forward(x_last, u_last, sim_dt) under hypothesis b's f_ext; err[b] = ||x_next[b] - x_curr||_2 in float64
+ *   with numpy's summation order; best = first argmin (:298-303)                                   (skipped when h_x_last == NULL: best = 0)
+ *   XU[:] = XU[best]  (:252-253) -- the batch of warm starts stays resident on the device between steps.
+ * The warm-start batch is solver-owned: seed it with gato_mpc_set_warm_start before the first step. */
+typedef struct gato_mpc_out {
+        int32_t       best_id;
+        double        best_error;
+        const double* errors;   /* [B], solver-owned, valid until the next step; all zero when scoring was skipped */
+        const float*  xu_best;  /* [traj], solver-owned pinned buffer: the selected trajectory */
+} gato_mpc_out;
+#define GATO_MPC_RESET_RHO 1
+int gato_mpc_set_warm_start(gato_solver* s, const float* h_xu /* [traj] tiled over the batch, or [B][traj] if per_solve */, int per_solve);
+int gato_mpc_set_state_offsets(gato_solver* s, const float* h_x_offset /* [B][nx] or NULL to clear */);
+int gato_mpc_step(gato_solver* s, const float* h_x_curr /*[nx]*/, const float* h_ref_window /*[6N]*/, const float* h_x_last /*[nx] or NULL*/,
+                  const float* h_u_last /*[nu] or NULL*/, float sim_dt, float timestep, int flags, gato_mpc_out* out, gato_stats* stats);
+int gato_mpc_get_warm_start(gato_solver* s, float* h_xu /*[B][traj]*/);
+
 /* Introspection */
 int  gato_dims(int plant, int knot_points, int* nx, int* nu, int* traj_size);
 long gato_kernel_launches(const gato_solver* s); /* kernels launched by this solver so far */
