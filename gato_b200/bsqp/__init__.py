@@ -62,11 +62,24 @@ def _make_class(plant, N, B):
                 "final_merit": r["final_merit"],
                 "initial_merit": r["initial_merit"],
                 "ls_num_iters": int(n_ls),
-                "pcg_times_us": np.zeros(n_ls, np.float32),
+                "pcg_times_us": self._pcg_times(n_ls),
                 "pcg_iters": r["pcg_iters"][:n_ls].astype(np.int32),
                 "ls_min_merit": r["ls_min_merit"],
                 "ls_step_size": r["ls_step_size"],
             }
+
+        def set_kernel_timing(self, enabled=True):
+            """Extension: with timing on, `pcg_times_us` holds the measured device time of each PCG kernel
+            (the reference fills it with zeros, bsqp.cuh:138)."""
+            self._timing = bool(enabled)
+            self._s.set_kernel_timing(self._timing)
+
+        def _pcg_times(self, n_ls):
+            out = np.zeros(n_ls, np.float32)
+            if getattr(self, "_timing", False):
+                t = [1e3 * ms for k, ms in self._s.launch_times() if k == "k_pcg"][:n_ls]
+                out[:len(t)] = t
+            return out
 
         def reset_dual(self):
             self._s.reset("dual")

@@ -189,3 +189,32 @@ def test_device_pointer_entry_and_async(backends):
     st = s.solve_device(xu.data_ptr(), xs.data_ptr(), rf.data_ptr(), w["dt"])
     assert n_mismatch(xu.cpu().numpy(), ref_out["XU"]) == 0 and np.array_equal(st["pcg_iters"], ref_out["pcg_iters"])
     assert st["device_time_ms"] > 0
+
+
+def test_kernel_timing_instrumentation_is_transparent():
+    """gato_set_kernel_timing / gato_get_kernel_times / gato_get_launch_times: event-per-launch timing does not change results, and the
+    Python mirror's opt-in `pcg_times_us` carries one measured PCG time per line search."""
+    from gato_b200.native import GatoBackend
+
+    g = GatoBackend("iiwa14", 32)
+    w = make_config(2, B=32)
+    a = g.solver(32, w["params"]).solve(w["xu"], w["xs"], w["ref"], w["dt"])
+    s = g.solver(32, w["params"])
+    s.set_kernel_timing(True)
+    b = s.solve(w["xu"], w["xs"], w["ref"], w["dt"])
+    assert n_mismatch(a["XU"], b["XU"]) == 0 and np.array_equal(a["pcg_iters"], b["pcg_iters"])
+    kt, lt = s.kernel_times(), s.launch_times()
+    n_it = int(w["params"]["max_sqp_iters"])
+    assert [kt[k][1] for k in ("k_kkt", "k_schur", "k_pcg", "k_merit_ls<8>", "k_merit_ls<1>")] == [n_it, n_it, n_it, n_it, 2]
+    assert all(ms > 0 for ms, _ in kt.values()) and len(lt) == 4 * n_it + 2 and lt[0][0] == "k_merit_ls<1>" and lt[1][0] == "k_kkt"
+    assert abs(sum(ms for _, ms in lt) - sum(ms for ms, _ in kt.values())) < 1e-3
+    from gato_b200.bsqp import bsqpN32_iiwa14 as mod
+    from gato_b200.native import PARAM_ORDER
+
+    p = w["params"]
+
+    slv = mod.BSQP_32_float(*[p[k] for k in PARAM_ORDER])
+    slv.set_kernel_timing(True)
+    r = slv.solve(w["xu"], float(w["dt"]), w["xs"], w["ref"])
+    assert r["pcg_times_us"].shape == (r["ls_num_iters"],) and (r["pcg_times_us"] > 0).all()
+    assert n_mismatch(r["XU"], a["XU"]) == 0
