@@ -8,7 +8,10 @@
 
 namespace gato {
 
-constexpr int kSchurWarps = 4;
+#ifndef GATO_SCHUR_WARPS
+#define GATO_SCHUR_WARPS 4
+#endif
+constexpr int kSchurWarps = GATO_SCHUR_WARPS;
 
 template<class P>
 void enqueue_kkt(const Ctx& c, cudaStream_t st);
