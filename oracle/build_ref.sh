@@ -3,7 +3,9 @@
 # they lie) into oracle/_ref/libgref_<plant>_N<N>_<fast|ieee>.so through oracle/ref_harness.cu.
 #   fast = the reference's own flags (CMakeLists.txt:20-22: -O3 -use_fast_math -DNDEBUG), arch swapped to sm_100
 #   ieee = same without -use_fast_math (isolates fast-math noise from algorithmic parity)
-# Usage: oracle/build_ref.sh [plant N batches mode]...   (no args: the default matrix below, in parallel)
+# Usage: oracle/build_ref.sh                 the library bench.py times (iiwa14 N=32)
+#        oracle/build_ref.sh all             every library oracle/gen_golden.py needs, in parallel
+#        oracle/build_ref.sh plant N batches mode [...]
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF=${GATO_REFERENCE_DIR:-/root/reference}
@@ -33,7 +35,12 @@ if [ $# -ge 4 ]; then
   exit 0
 fi
 
-# default matrix (BASELINE.json configs + the bench shape)
+# no arguments: the one library the GPU box needs at run time (bench.py's reference_gpu row: iiwa14, N=32, B=512, the reference's flags).
+# "all": the whole matrix oracle/gen_golden.py uses to mint tests/golden/ (BASELINE.json configs + the bench shape; ~15 min on 6 jobs).
+if [ "${1:-}" != all ]; then
+  build_one iiwa14 32 16,128,512 fast
+  exit 0
+fi
 JOBS=${GREF_JOBS:-6}
 cat <<LIST | xargs -P "$JOBS" -L 1 "$0"
 iiwa14 32 16,128,512 fast

@@ -2,7 +2,7 @@
 """TEST INFRASTRUCTURE — mint golden vectors by RUNNING THE REFERENCE ITSELF on the B200 box.
 
 Runs on the GPU box under gpurun (needs only oracle/_ref/*.so built from the unmodified reference by
-oracle/build_ref.sh, numpy and gato_b200.workloads; /root/reference is NOT read).  Writes
+`oracle/build_ref.sh all`, numpy and gato_b200.workloads; /root/reference is NOT read).  Writes
 gpurun_out/golden/golden_<plant>_N<N>_<mode>.npz (+ meta.json, + reference timings); the files are then
 copied into tests/golden/ and committed.
 
