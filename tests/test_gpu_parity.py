@@ -34,7 +34,7 @@ def _inputs(cfg, B, N, seed=11):
     return w, xu, fext
 
 
-@pytest.mark.parametrize("plant,N,cfg,B", [("iiwa14", 8, 1, 3), ("iiwa14", 32, 2, 5), ("indy7", 32, 3, 4), ("indy7", 16, 3, 2), ("iiwa14", 16, 2, 33), ("iiwa14", 128, 4, 2), ("indy7", 64, 3, 2)])
+@pytest.mark.parametrize("plant,N,cfg,B", [("iiwa14", 8, 1, 3), ("iiwa14", 32, 2, 5), ("indy7", 32, 3, 4), ("indy7", 16, 3, 2), ("iiwa14", 16, 2, 33), ("iiwa14", 128, 4, 2), ("indy7", 64, 3, 2), ("iiwa14", 9, 2, 3), ("indy7", 7, 3, 2), ("iiwa14", 3, 1, 2)])
 def test_every_stage_bit_exact_vs_oracle(backends, plant, N, cfg, B):
     o, g = backends(plant, N)
     d = o.d
@@ -76,7 +76,7 @@ def test_every_stage_bit_exact_vs_oracle(backends, plant, N, cfg, B):
             assert n_mismatch(lsg[k], lso[k]) == 0, f"line search {k}"
 
 
-@pytest.mark.parametrize("plant,N,cfg,B", [("iiwa14", 8, 1, 1), ("iiwa14", 32, 2, 16), ("indy7", 32, 3, 16), ("iiwa14", 32, 5, 16), ("iiwa14", 128, 4, 4)])
+@pytest.mark.parametrize("plant,N,cfg,B", [("iiwa14", 8, 1, 1), ("iiwa14", 32, 2, 16), ("indy7", 32, 3, 16), ("iiwa14", 32, 5, 16), ("iiwa14", 128, 4, 4), ("iiwa14", 9, 2, 5), ("indy7", 33, 3, 3)])
 def test_whole_solve_bit_exact_vs_oracle(backends, plant, N, cfg, B):
     o, g = backends(plant, N)
     w = make_config(cfg, B=B, N=N)
@@ -218,3 +218,34 @@ def test_kernel_timing_instrumentation_is_transparent():
     r = slv.solve(w["xu"], float(w["dt"]), w["xs"], w["ref"])
     assert r["pcg_times_us"].shape == (r["ls_num_iters"],) and (r["pcg_times_us"] > 0).all()
     assert n_mismatch(r["XU"], a["XU"]) == 0
+
+
+@pytest.mark.parametrize("cfg,subset", [(3, 6), (4, 3), (5, 6)])
+def test_baseline_configs_at_full_size(backends, cfg, subset):
+    """BASELINE.json configs 3 (indy7, N=32, B=512), 4 (iiwa14, N=128, B=1024) and 5 (iiwa14, N=32, B=1024 per GPU, per-solve rho / mu)
+    at their full sizes: determinism, merit never increased by accepted steps, and -- because solves are independent (checked bit-for-bit
+    in test_full_size_properties) -- a handful of solves out of the full batch compared bit-for-bit with the CPU oracle run on just those."""
+    w = make_config(cfg)
+    B, N, plant = w["B"], w["N"], w["plant"]
+    o, g = backends(plant, N)
+
+    def setup(s, sl):
+        for key in ("rho", "mu"):
+            if key in w["extra"]:
+                s.set_batch(key, w["extra"][key][sl])
+
+    sg = g.solver(B, w["params"])
+    setup(sg, slice(None))
+    a = sg.solve(w["xu"], w["xs"], w["ref"], w["dt"])
+    assert np.isfinite(a["XU"]).all() and (a["final_merit"] <= a["initial_merit"] * (1 + 1e-6) + 1e-6).all()
+    sg.reset("dual"), sg.reset("rho")
+    b = sg.solve(w["xu"], w["xs"], w["ref"], w["dt"])
+    assert n_mismatch(a["XU"], b["XU"]) == 0 and np.array_equal(a["pcg_iters"], b["pcg_iters"])
+    idx = np.linspace(0, B - 1, subset).astype(int)
+    p1 = dict(w["params"], solve_ratio=2.0)  # the early-exit count is per batch: disable it for the subset comparison if it never fired
+    if a["n_pcg"] == int(w["params"]["max_sqp_iters"]) and a["n_ls"] == a["n_pcg"]:
+        so = o.solver(len(idx), p1)
+        setup(so, idx)
+        ro = so.solve(w["xu"][idx], w["xs"][idx], w["ref"][idx], w["dt"])
+        assert n_mismatch(ro["XU"], a["XU"][idx]) == 0
+        assert np.array_equal(ro["pcg_iters"], a["pcg_iters"][:, idx]) and np.array_equal(ro["ls_step_size"], a["ls_step_size"][:, idx])
