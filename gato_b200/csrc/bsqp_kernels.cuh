@@ -1,9 +1,12 @@
 // CUDA kernels of the B200-native BSQP solve path (sm_100a).  One SQP iteration is four launches:
 //
-//   k_kkt       thread per (solve, knot)      linearise dynamics + quadraticise cost      -> A,B,c,Q,R,q,r (HBM/L2)
-//   k_schur     warp   per (solve, knot)      Gauss-Jordan inverses, phi/theta/gamma       -> S, diag(P^-1), gamma, Q^-1, R^-1
-//   k_pcg       CTA    per solve              S,P^-1 resident in shared memory; off-diagonal P^-1 blocks, PCG,
-//                                             primal step dz, device-side convergence bookkeeping
+//   k_kkt       thread per work item          linearise dynamics + quadraticise cost      -> A,B,c,Q,R,q,r (HBM/L2)
+//               (cost block of a knot / d-dq half / d-dqd half of a linearisation, one kind per warp)
+//   k_schur     warp   per pair of knots      in-place Gauss-Jordan inverses (two matrices per pass), phi/theta/gamma
+//                                             -> S, diag(P^-1), gamma, Q^-1, R^-1
+//   k_pcg       CTA    per solve              each thread keeps its rows of S and P^-1 in registers; off-diagonal P^-1 blocks,
+//                                             PCG, primal step dz, device-side convergence bookkeeping
+//               (k_pcg_stream for horizons whose system does not fit the register file)
 //   k_merit_ls  CTA    per solve              8 x N forward-dynamics merit evaluations (thread per (alpha, knot)),
 //                                             deterministic knot-ordered sum, line search, trajectory/rho update
 //
@@ -172,6 +175,117 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
                         flush(c.Bm, rX, NX * NU, NX * NU, 0, 0, 2);
                 }
         }
+}
+
+// =====================================================================================================
+// k_kkt_fine: the same work cut finer, for small batches (the MPC regime) where k_kkt's three kinds leave most of the GPU idle and the
+// time of a launch is the latency of one thread's instruction stream: 2 + 2 nq kinds (blockIdx.y) --
+//   kind 0       cost blocks (as k_kkt)                     kind 1            B_k and the defect c_{k+1}
+//   kind 2+j     column j of A_k (d/dq_j)                   kind 2+nq+j       column nq+j of A_k (d/dqd_j)
+// every dynamics kind repeats the prologue; a thread then runs about 40 % of the instructions of a k_kkt thread.
+// =====================================================================================================
+template<class P>
+__global__ void __launch_bounds__(32) k_kkt_fine(Ctx c)
+{
+        constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ, ST = 33;
+        constexpr int ROWS = NX * NU + NX;  // kind 1 stages the most: B | c
+        static_assert(ROWS >= NQ * NQ + NQ + NX + NU + NU + NX, "kind 0 fits");
+        if (stopped_before(c, c.it)) return;
+        __shared__ float stage[ROWS * ST];
+        const int        kind = blockIdx.y;
+        const int        lane = threadIdx.x;
+        const int        item0 = blockIdx.x * 32;
+        const int        per = (kind == 0) ? c.N : c.N - 1;
+        const int        total = c.B * per;
+        if (item0 >= total) return;
+        const int  item = item0 + lane;
+        const bool valid = item < total;
+        const int  b = valid ? item / per : 0, k = valid ? item % per : 0;
+        const bool term = (kind == 0) && (k == c.N - 1);
+        const int  traj = (NX + NU) * c.N - NU;
+        const int  ks = term ? k - 1 : k;
+        float      xux[2 * NX + NU];
+        {
+                const float* src = c.xu + (size_t)b * traj + (size_t)ks * (NX + NU);
+                sfor<0, 2 * NX + NU>([&](auto ic) { xux[ic] = src[ic]; });
+        }
+        auto flush = [&](float* dst, int row0, int count, int stride, int off, int koff, int which) {
+                const int nvalid = min(32, total - item0);
+                for (int i = 0; i < nvalid; i++) {
+                        const int  it_ = item0 + i, bi = it_ / per, ki = it_ % per;
+                        const bool ti = (kind == 0) && (ki == c.N - 1);
+                        if ((which == 0 && ti) || (which == 1 && !ti)) continue;
+                        float* d = dst + ((size_t)bi * c.N + ki + koff) * stride + off;
+                        for (int e = lane; e < count; e += 32) d[e] = stage[(row0 + e) * ST + i];
+                }
+        };
+        if (kind == 0) {
+                float ref3[3];
+                sfor<0, 3>([&](auto ic) { ref3[ic] = c.ref[(size_t)b * 6 * c.N + 6 * k + ic]; });
+                constexpr int rQ = 0, rQd = NQ * NQ, rq = rQd + NQ, rR = rq + NX, rr = rR + NU, rc0 = rr + NU;
+                Items<P>::template cost_grad_hess<true>(
+                    xux, ref3, c.cs,
+                    [&](int e, float v) {
+                            const int i = e / NX, j = e % NX;
+                            if (i < NQ && j < NQ)
+                                    stage[(rQ + i * NQ + j) * ST + lane] = v;
+                            else if (i == j)
+                                    stage[(rQd + i - NQ) * ST + lane] = v;
+                    },
+                    [&](int e, float v) { stage[(rq + e) * ST + lane] = v; },
+                    [&](int e, float v) {
+                            if (e / NU == e % NU) stage[(rR + e / NU) * ST + lane] = v;
+                    },
+                    [&](int e, float v) { stage[(rr + e) * ST + lane] = v; });
+                if (term && valid) {
+                        const float* x0 = c.xu + (size_t)b * traj;
+                        sfor<0, NX>([&](auto ic) { stage[(rc0 + ic) * ST + lane] = x0[ic] - c.xs[(size_t)b * NX + ic]; });
+                }
+                __syncwarp();
+                {
+                        const int nvalid = min(32, total - item0);
+                        for (int i = 0; i < nvalid; i++) {
+                                const int it_ = item0 + i, bi = it_ / per, ki = it_ % per;
+                                float*    dQ = c.Q + ((size_t)bi * c.N + ki) * NX * NX;
+                                for (int e = lane; e < NX * NX; e += 32) {
+                                        const int r_ = e / NX, c_ = e % NX;
+                                        float     v = 0.0f;
+                                        if (r_ < NQ && c_ < NQ)
+                                                v = stage[(rQ + r_ * NQ + c_) * ST + i];
+                                        else if (r_ == c_)
+                                                v = stage[(rQd + r_ - NQ) * ST + i];
+                                        dQ[e] = v;
+                                }
+                                if (ki != c.N - 1) {
+                                        float* dR = c.R + ((size_t)bi * c.N + ki) * NU * NU;
+                                        for (int e = lane; e < NU * NU; e += 32) dR[e] = (e / NU == e % NU) ? stage[(rR + e / NU) * ST + i] : 0.0f;
+                                }
+                        }
+                }
+                flush(c.q, rq, NX, NX, 0, 0, 2);
+                flush(c.r, rr, NU, NU, 0, 0, 0);
+                flush(c.c, rc0, NX, NX, 0, -(c.N - 1), 1);
+                return;
+        }
+        float fext[6];
+        sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * b + ic]; });
+        typename Rbd<P>::DynState st;
+        Rbd<P>::dyn_prologue(xux, xux + NQ, xux + NX, fext, st);
+        if (kind == 1) {
+                constexpr int rB = 0, rc = NX * NU;
+                Items<P>::linearize_base(st, xux, c.dt, [&](int e, float v) { stage[(rB + e) * ST + lane] = v; }, [&](int e, float v) { stage[(rc + e) * ST + lane] = v; });
+                __syncwarp();
+                flush(c.Bm, rB, NX * NU, NX * NU, 0, 0, 2);
+                flush(c.c, rc, NX, NX, 0, 1, 2);
+                return;
+        }
+        const int col = kind - 2;  // column of A
+        sfor<0, NX>([&](auto cc) {
+                constexpr int cidx = cc;
+                if (col == cidx) Items<P>::template linearize_column<cidx / NQ, cidx % NQ>(st, xux + NQ, c.dt, [&](int e, float v) { stage[(e - cidx * NX) * ST + lane] = v; });
+        });
+        __syncwarp();
+        flush(c.A, 0, NX, NX * NX, col * NX, 0, 2);
 }
 
 #include "bsqp_linalg_kernels.cuh"  // k_schur, k_pcg

@@ -229,9 +229,10 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
                 c.flags = F_CHECK_STOP | F_MERIT | F_LS;
                 launch_merit<P, kNumAlphas>(s, c);
         }
-        // final merit on the updated trajectory  bsqp.cuh:180-182
-        c.flags = F_MERIT | F_ZERO_DZ;
-        launch_merit<P, 1>(s, c);
+        // Final merit on the updated trajectory (bsqp.cuh:180-182): no launch needed.  merit_cur[b] already holds it bit-for-bit: it is the
+        // merit of the last accepted line-search candidate, evaluated by k_merit_ls<8> at exactly the trajectory fmaf(step, dz, xu) that the
+        // line search then stored (same expression, same knot-ordered sum), or -- if no step was ever accepted -- the initial merit of the
+        // unchanged trajectory.  (The reference re-evaluates it with a fresh kernel.)
         tick(s, -1);
         CUDA_TRY(s, cudaGetLastError());
         // results -> pinned host buffers

@@ -157,6 +157,52 @@ struct Items {
                 }
         }
 
+        // ---- the same linearisation one column per thread (small batches: k_kkt_fine) -------------------------------------------------
+        // column c = K + W*NQ of A (W = 0: d/dq_K, W = 1: d/dqd_K); bit-identical to linearize() / linearize_half()
+        template<int W, int K, class FA>
+        static GATO_HD void linearize_column(const typename R::DynState& st, const float* qd, float dt, FA&& putA)
+        {
+                float dc[NQ], d[NQ];
+                R::template rnea_grad_col<W, K>(st.X, qd, st.v, st.a, st.f, st.Iv, st.FxvI, dc);
+                sfor<0, NQ>([&](auto rc) {
+                        constexpr int row = rc;
+                        float         val = 0.0f;
+                        sfor<0, NQ>([&](auto cc) { val = fmaf(R::template minv_sym<row, cc>(st.Minv), dc[cc], val); });
+                        d[row] = -val;
+                });
+                const float   dt_sq_half = (float)((0.5 * (double)dt) * (double)dt);
+                constexpr int c = K + W * NQ;
+                sfor<0, NX>([&](auto rc) {
+                        constexpr int r = rc, rd = r % NQ;
+                        float         val = (r == c) ? 1.0f : 0.0f;
+                        if constexpr (r < NQ) {
+                                if constexpr (c >= NQ && r == c - NQ) val = val + dt;
+                                val = fmaf(dt_sq_half, d[rd], val);
+                        } else {
+                                val = fmaf(dt, d[rd], val);
+                        }
+                        putA(c * NX + r, val);
+                });
+        }
+        // B (from M^-1) and the defect c_{k+1}
+        template<class FB, class Fc>
+        static GATO_HD void linearize_base(const typename R::DynState& st, const float* xux, float dt, FB&& putB, Fc&& putc)
+        {
+                const float dt_sq_half = (float)((0.5 * (double)dt) * (double)dt);
+                float       qn[NQ], qdn[NQ];
+                R::integrate(xux, xux + NQ, st.qdd, dt, qn, qdn);
+                sfor<0, NQ>([&](auto ic) {
+                        constexpr int i = ic;
+                        putc(i, xux[NX + NU + i] - qn[i]);
+                        putc(i + NQ, xux[NX + NU + NQ + i] - qdn[i]);
+                });
+                sfor<0, NX * NU>([&](auto ec) {
+                        constexpr int i = ec, c = i / NX, r = i % NX, rd = r % NQ;
+                        const float   d = R::template minv_sym<rd, c>(st.Minv);
+                        putB(i, (r < NQ) ? (dt_sq_half * d) : (dt * d));
+                });
+        }
+
         // ---- merit contribution of knot k ------------------------------------------------------------------
         // xux = z + alpha dz at knot k: x_k,u_k,x_{k+1} (k < N-1) or x_{N-1} only; x0err = |x_0 + alpha dz_0 - x_s| entries (used at k = N-1)
         template<bool LAST>

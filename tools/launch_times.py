@@ -1,5 +1,5 @@
 """Per-launch CUDA-event durations of one solve of the bench workload (run on a GPU box): shows how each kernel's time changes
-from the first SQP iteration (cold L2 after the flush) to the later ones.   usage: python tools/launch_times.py [batch]"""
+from the first SQP iteration (cold L2 after the flush) to the later ones.   usage: python tools/launch_times.py [batch [knot_points]]"""
 import sys
 
 sys.path.insert(0, ".")
@@ -10,7 +10,8 @@ from gato_b200 import native
 from gato_b200.workloads import make_config
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-w = make_config("bench", B=B)
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+w = make_config("bench", B=B, N=N)
 xu0 = torch.from_numpy(w["xu"].copy()).cuda()
 xs = torch.from_numpy(w["xs"].copy()).cuda()
 ref = torch.from_numpy(w["ref"].copy()).cuda()
