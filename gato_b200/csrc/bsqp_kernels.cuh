@@ -162,13 +162,13 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
                 sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * b + ic]; });
                 constexpr int rA = 0, rX = NX * NQ;  // half of A (NX*NQ contiguous floats), then c (kind 1) or B (kind 2)
                 if (kind == 1) {
-                        Items<P>::template linearize_half<0>(
+                        Items<P>::template linearize_half_rolled<0>(
                             xux, fext, c.dt, [&](int e, float v) { stage[(rA + e) * ST + lane] = v; }, [&](int, float) {}, [&](int e, float v) { stage[(rX + e) * ST + lane] = v; });
                         __syncwarp();
                         flush(c.A, rA, NX * NQ, NX * NX, 0, 0, 2);
                         flush(c.c, rX, NX, NX, 0, 1, 2);
                 } else {
-                        Items<P>::template linearize_half<1>(
+                        Items<P>::template linearize_half_rolled<1>(
                             xux, fext, c.dt, [&](int e, float v) { stage[(rA + e - NX * NQ) * ST + lane] = v; }, [&](int e, float v) { stage[(rX + e) * ST + lane] = v; }, [&](int, float) {});
                         __syncwarp();
                         flush(c.A, rA, NX * NQ, NX * NX, NX * NQ, 0, 2);

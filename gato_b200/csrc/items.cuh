@@ -157,6 +157,55 @@ struct Items {
                 }
         }
 
+        // ---- linearize_half with the loop over the columns rolled (rnea_grad_col_rt): what k_kkt runs -----------------------------------
+        template<int HALF, class FA, class FB, class Fc>
+        static GATO_HD void linearize_half_rolled(const float* xux, const float* fext, float dt, FA&& putA, FB&& putB, Fc&& putc)
+        {
+                typename R::DynState st;
+                R::dyn_prologue(xux, xux + NQ, xux + NX, fext, st);
+                const float dt_sq_half = (float)((0.5 * (double)dt) * (double)dt);
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+                for (int k = 0; k < NQ; k++) {
+                        float dc[NQ], d[NQ];
+                        R::template rnea_grad_col_rt<HALF>(k, st.X, xux + NQ, st.v, st.a, st.f, st.Iv, st.FxvI, dc);
+                        sfor<0, NQ>([&](auto rc) {
+                                constexpr int row = rc;
+                                float         val = 0.0f;
+                                sfor<0, NQ>([&](auto cc) { val = fmaf(R::template minv_sym<row, cc>(st.Minv), dc[cc], val); });
+                                d[row] = -val;
+                        });
+                        const int c = k + HALF * NQ;
+                        sfor<0, NX>([&](auto rc) {
+                                constexpr int r = rc, rd = r % NQ;
+                                float         val = (r == c) ? 1.0f : 0.0f;
+                                if constexpr (r < NQ) {
+                                        if (HALF == 1 && r == k) val = val + dt;  // c >= NQ && r == c - NQ
+                                        val = fmaf(dt_sq_half, d[rd], val);
+                                } else {
+                                        val = fmaf(dt, d[rd], val);
+                                }
+                                putA(c * NX + r, val);
+                        });
+                }
+                if constexpr (HALF == 0) {
+                        float qn[NQ], qdn[NQ];
+                        R::integrate(xux, xux + NQ, st.qdd, dt, qn, qdn);
+                        sfor<0, NQ>([&](auto ic) {
+                                constexpr int i = ic;
+                                putc(i, xux[NX + NU + i] - qn[i]);
+                                putc(i + NQ, xux[NX + NU + NQ + i] - qdn[i]);
+                        });
+                } else {
+                        sfor<0, NX * NU>([&](auto ec) {
+                                constexpr int i = ec, c = i / NX, r = i % NX, rd = r % NQ;
+                                const float   d = R::template minv_sym<rd, c>(st.Minv);
+                                putB(i, (r < NQ) ? (dt_sq_half * d) : (dt * d));
+                        });
+                }
+        }
+
         // ---- the same linearisation one column per thread (small batches: k_kkt_fine) -------------------------------------------------
         // column c = K + W*NQ of A (W = 0: d/dq_K, W = 1: d/dqd_K); bit-identical to linearize() / linearize_half()
         template<int W, int K, class FA>

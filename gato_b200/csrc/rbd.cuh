@@ -453,6 +453,83 @@ struct Rbd {
                 sfor<0, NQ>([&](auto jc) { dc[jc] = df[jc][2]; });
         }
 
+        // The same column with K as a RUN-TIME value (uniform across the warp): one copy of the per-joint code serves all columns, so a
+        // loop over k re-executes ~2k instructions that stay in the instruction caches instead of streaming 7 specialised copies (the
+        // fully unrolled gradient is instruction-fetch bound).  Joints below k are skipped by uniform branches; every operation that is
+        // executed is the one rnea_grad_col<W, k> executes, on the same values.
+        template<int W>
+        static GATO_HD void rnea_grad_col_rt(int k, const Xmat& X, const float* qd, const V6& v, const V6& a, const V6& f, const V6& Iv, const float (&FxvI)[NQ][36], float (&dc)[NQ])
+        {
+                float df[NQ][6];
+                float dv[6], da[6];
+                sfor<0, NQ>([&](auto jc) { sfor<0, 6>([&](auto rc) { df[jc][rc] = 0.0f; }); });
+                sfor<0, 6>([&](auto rc) { dv[rc] = 0.0f, da[rc] = 0.0f; });
+                sfor<0, NQ>([&](auto jc) {
+                        constexpr int j = jc;
+                        if (j >= k) {
+                                float ndv[6], nda[6];
+                                if (j == k) {
+                                        float src[6];
+                                        if constexpr (W == 0) {
+                                                float Xv[6], Xa[6];
+                                                sfor<0, 6>([&](auto rc) {
+                                                        constexpr int row = rc;
+                                                        if constexpr (j == 0) {
+                                                                Xv[row] = 0.0f;
+                                                                Xa[row] = XE<P, 0, row, 5>::nz ? xv<0, row, 5>(X) * kGravity : 0.0f;
+                                                        } else {
+                                                                Xv[row] = xrow<j, row>(X, v[j > 0 ? j - 1 : 0]);
+                                                                Xa[row] = xrow<j, row>(X, a[j > 0 ? j - 1 : 0]);
+                                                        }
+                                                });
+                                                ndv[0] = Xv[1], ndv[1] = -Xv[0], ndv[2] = 0.0f, ndv[3] = Xv[4], ndv[4] = -Xv[3], ndv[5] = 0.0f;
+                                                src[0] = Xa[1], src[1] = -Xa[0], src[2] = 0.0f, src[3] = Xa[4], src[4] = -Xa[3], src[5] = 0.0f;
+                                                if constexpr (j == 0) sfor<0, 6>([&](auto rc) { ndv[rc] = 0.0f; });
+                                        } else {
+                                                sfor<0, 6>([&](auto rc) { ndv[rc] = (rc == 2) ? 1.0f : 0.0f; });
+                                                src[0] = v[j][1], src[1] = -v[j][0], src[2] = 0.0f, src[3] = v[j][4], src[4] = -v[j][3], src[5] = 0.0f;
+                                        }
+                                        nda[0] = ndv[1] * qd[j], nda[1] = (-ndv[0]) * qd[j], nda[2] = 0.0f, nda[3] = ndv[4] * qd[j], nda[4] = (-ndv[3]) * qd[j], nda[5] = 0.0f;
+                                        sfor<0, 6>([&](auto rc) { nda[rc] = nda[rc] + src[rc]; });
+                                } else {
+                                        if constexpr (j > 0) {
+                                                sfor<0, 6>([&](auto rc) { ndv[rc] = xrow<j, rc>(X, dv); });
+                                                nda[0] = ndv[1] * qd[j], nda[1] = (-ndv[0]) * qd[j], nda[2] = 0.0f, nda[3] = ndv[4] * qd[j], nda[4] = (-ndv[3]) * qd[j], nda[5] = 0.0f;
+                                                sfor<0, 6>([&](auto rc) { nda[rc] = nda[rc] + xrow<j, rc>(X, da); });
+                                        } else {
+                                                sfor<0, 6>([&](auto rc) { ndv[rc] = 0.0f, nda[rc] = 0.0f; });  // unreachable: j > k >= 0
+                                        }
+                                }
+                                sfor<0, 6>([&](auto rc) {
+                                        dv[rc] = ndv[rc];
+                                        da[rc] = nda[rc];
+                                });
+                                float t0[6];
+                                fx_times_v(t0, dv, Iv[j]);
+                                sfor<0, 6>([&](auto rc) {
+                                        constexpr int row = rc;
+                                        float         d1 = irow<j, row>(da);
+                                        float         d2 = 0.0f;
+                                        sfor<0, 6>([&](auto tc) { d2 = fmaf(FxvI[j][row + 6 * tc], dv[tc], d2); });
+                                        df[j][row] = t0[row] + (d1 + d2);
+                                });
+                        }
+                });
+                sfor_down<1, NQ>([&](auto jc) {
+                        constexpr int j = jc;
+                        float         upd[6];
+                        sfor<0, 6>([&](auto rc) { upd[rc] = xcol<j, rc>(X, df[j]); });
+                        if constexpr (W == 0) {
+                                if (k == j) {
+                                        float mxf[6] = {f[j][1], -f[j][0], 0.0f, f[j][4], -f[j][3], 0.0f};
+                                        sfor<0, 6>([&](auto rc) { upd[rc] = upd[rc] + (-xcol<j, rc>(X, mxf)); });
+                                }
+                        }
+                        sfor<0, 6>([&](auto rc) { df[j - 1][rc] = df[j - 1][rc] + upd[rc]; });
+                });
+                sfor<0, NQ>([&](auto jc) { dc[jc] = df[jc][2]; });
+        }
+
         // forwardDynamicsAndGradient with wrench (iiwa14_plant.cuh:229-268), split so that the column blocks of the gradient can be
         // computed by different threads: dyn_prologue (X, M^-1, RNEA, qdd, RNEA with qdd, I v, fx(v) I) + grad_block<W>.
         struct DynState {
