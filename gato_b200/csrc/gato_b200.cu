@@ -131,7 +131,8 @@ int configure_kernels(gato_solver* s)
                         return GATO_ERR_UNSUPPORTED;
                 }
                 s->pcg_threads = 1024;
-                s->smem_pcg = sizeof(float) * ((size_t)2 * n + 64 + 64 * 32 + (size_t)(s->N - 1) * 4 * P::NQ * P::NQ);
+                // vectors | dot scratch | dz scratch | max(K2 scratch, 32 per-warp tiles of 32 rows x 3nx floats)
+                s->smem_pcg = sizeof(float) * ((size_t)2 * n + 64 + 64 * 32 + std::max((size_t)(s->N - 1) * 4 * P::NQ * P::NQ, (size_t)32 * 32 * 6 * P::NQ));
         } else {
                 s->smem_pcg = pcg_smem_bytes<P>(s->N, s->pcg_threads);
         }
