@@ -249,3 +249,37 @@ def test_baseline_configs_at_full_size(backends, cfg, subset):
         ro = so.solve(w["xu"][idx], w["xs"][idx], w["ref"][idx], w["dt"])
         assert n_mismatch(ro["XU"], a["XU"][idx]) == 0
         assert np.array_equal(ro["pcg_iters"], a["pcg_iters"][:, idx]) and np.array_equal(ro["ls_step_size"], a["ls_step_size"][:, idx])
+
+
+def test_randomized_whole_solves_bit_exact(backends):
+    """Randomised sweep (fixed seeds): horizon, batch, plant, cost weights, rho / mu / f_ext batches and large-amplitude states (sin/cos range
+    reduction, barrier logs near the joint limits, tiny pivots in the elimination) -- whole solves bit-for-bit against the oracle."""
+    for seed in range(12):
+        rng = np.random.default_rng(1000 + seed)
+        plant = "iiwa14" if rng.random() < 0.6 else "indy7"
+        N = int(rng.integers(3, 41))
+        B = int(rng.integers(1, 10))
+        o, g = backends(plant, N)
+        nq = o.d["nq"]
+        w = make_config(2 if plant == "iiwa14" else 3, B=B, N=N)
+        p = dict(w["params"], max_sqp_iters=int(rng.integers(1, 4)), max_pcg_iters=int(rng.integers(1, 60)), pcg_tol=float(10 ** rng.uniform(-6, -2)),
+                 mu=float(10 ** rng.uniform(-1, 2)), q_cost=float(10 ** rng.uniform(-1, 1)), qd_cost=float(10 ** rng.uniform(-3, -1)), u_cost=float(10 ** rng.uniform(-7, -4)),
+                 N_cost=float(10 ** rng.uniform(0, 2)), q_lim_cost=float(rng.choice([0.0, 0.01, 0.1])), vel_lim_cost=float(rng.choice([0.0, 0.002])),
+                 ctrl_lim_cost=float(rng.choice([0.0, 0.001])), rho=float(10 ** rng.uniform(-6, 0)), solve_ratio=float(rng.choice([1.0, 0.5])))
+        scale = float(rng.choice([0.05, 0.5, 2.0]))
+        xu = (w["xu"] + rng.normal(0, scale, w["xu"].shape)).astype(np.float32)
+        xs = (w["xs"] + rng.normal(0, 0.1, w["xs"].shape)).astype(np.float32)
+        so, sg = o.solver(B, p), g.solver(B, p)
+        fext = rng.normal(0, 3, (B, 6)).astype(np.float32) if seed % 2 else np.zeros((B, 6), np.float32)
+        mu = rng.choice([1.0, 10.0, 100.0], B).astype(np.float32)
+        for s in (so, sg):
+            s.set_batch("f_ext", fext)
+            s.set_batch("rho", np.logspace(-6, 0, B).astype(np.float32), True)
+            s.set_batch("mu", mu)
+        ro, rg = so.solve(xu, xs, w["ref"], w["dt"]), sg.solve(xu, xs, w["ref"], w["dt"])
+        tag = f"seed {seed}: {plant} N={N} B={B}"
+        assert (rg["n_pcg"], rg["n_ls"]) == (ro["n_pcg"], ro["n_ls"]), tag
+        for k in ("pcg_iters", "sqp_iters", "kkt_converged"):
+            assert np.array_equal(rg[k], ro[k]), f"{tag} {k}"
+        for k in ("XU", "ls_step_size", "ls_min_merit", "final_merit", "initial_merit"):
+            assert n_mismatch(rg[k], ro[k]) == 0, f"{tag} {k}"
