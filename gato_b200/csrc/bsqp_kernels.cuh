@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
                     [&](int e, float v) {
                             if (e / NU == e % NU) stage[(rR + e / NU) * ST + lane] = v;
                     },
-                    [&](int e, float v) { stage[(rr + e) * ST + lane] = v; });
+                    [&](int e, float v) { stage[(rr + e) * ST + lane] = v; }, term, term || Items<P>::pos_form_b_for(c.N));
                 if (term && valid) {
                         const float* x0 = c.xu + (size_t)b * traj;
                         sfor<0, NX>([&](auto ic) { stage[(rc0 + ic) * ST + lane] = x0[ic] - c.xs[(size_t)b * NX + ic]; });
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(32) k_kkt_fine(Ctx c)
                     [&](int e, float v) {
                             if (e / NU == e % NU) stage[(rR + e / NU) * ST + lane] = v;
                     },
-                    [&](int e, float v) { stage[(rr + e) * ST + lane] = v; });
+                    [&](int e, float v) { stage[(rr + e) * ST + lane] = v; }, term, term || Items<P>::pos_form_b_for(c.N));
                 if (term && valid) {
                         const float* x0 = c.xu + (size_t)b * traj;
                         sfor<0, NX>([&](auto ic) { stage[(rc0 + ic) * ST + lane] = x0[ic] - c.xs[(size_t)b * NX + ic]; });

@@ -19,8 +19,14 @@ struct Items {
         static constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ;
 
         // ---- tracking cost gradient / Hessian at (x,u) against ref xyz, weight q_cost (see oracle note) ----
+        // terminal: the block is Q_{N-1}, q_{N-1} (the reference's computeR = false instantiation).  pos_form_b: the position entries of the
+        // gradient use fma(lim, barrier', round(a * b)) instead of fma(a, b, round(lim * barrier')) -- what nvcc emits for the terminal block
+        // and, when the reference is compiled for a horizon of 4 ... 9 knots, for every block (see the oracle's cost_grad_hess).
+        static constexpr int kPosFormBMinKnots = 4, kPosFormBMaxKnots = 9;
+        static GATO_HD bool pos_form_b_for(int knot_points) { return knot_points >= kPosFormBMinKnots && knot_points <= kPosFormBMaxKnots; }
         template<bool WITH_R, class FQ, class Fq, class FR, class Fr>
-        static GATO_HD void cost_grad_hess(const float* xu, const float* ref3, const Costs& cs, FQ&& putQ, Fq&& putq, FR&& putR, Fr&& putr)
+        static GATO_HD void cost_grad_hess(const float* xu, const float* ref3, const Costs& cs, FQ&& putQ, Fq&& putq, FR&& putR, Fr&& putr, bool terminal = !WITH_R,
+                                           bool pos_form_b = !WITH_R)
         {
                 float ee[3], J[NQ][3], e[3], h[NQ];
                 R::ee_pos_grad(xu, ee, J);
@@ -37,8 +43,8 @@ struct Items {
                         constexpr int i = ic;
                         bq[i] = R::joint_barrier_grad(xu[i], limit<P, 0, i, 0>(), limit<P, 0, i, 1>());
                         bv[i] = R::joint_barrier_grad(xu[NQ + i], limit<P, 1, i, 0>(), limit<P, 1, i, 1>());
-                        putq(i, fmaf(h[i], w, cs.q_lim_cost * bq[i]));
-                        putq(NQ + i, fmaf(cs.qd_cost, xu[NQ + i], cs.vel_lim_cost * bv[i]));
+                        putq(i, pos_form_b ? fmaf(cs.q_lim_cost, bq[i], h[i] * w) : fmaf(h[i], w, cs.q_lim_cost * bq[i]));
+                        putq(NQ + i, terminal ? fmaf(cs.vel_lim_cost, bv[i], cs.qd_cost * xu[NQ + i]) : fmaf(cs.qd_cost, xu[NQ + i], cs.vel_lim_cost * bv[i]));
                         if constexpr (WITH_R) {
                                 bu[i] = R::joint_barrier_grad(xu[NX + i], limit<P, 2, i, 0>(), limit<P, 2, i, 1>());
                                 putr(i, fmaf(cs.u_cost, xu[NX + i], cs.ctrl_lim_cost * bu[i]));

@@ -5,6 +5,7 @@
 #   ieee = same without -use_fast_math (isolates fast-math noise from algorithmic parity)
 # Usage: oracle/build_ref.sh                 the library bench.py times (iiwa14 N=32)
 #        oracle/build_ref.sh all             every library oracle/gen_golden.py needs, in parallel
+#        oracle/build_ref.sh pin             the IEEE builds the tools/pin_*.py comparisons use
 #        oracle/build_ref.sh plant N batches mode [...]
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -37,6 +38,12 @@ fi
 
 # no arguments: the one library the GPU box needs at run time (bench.py's reference_gpu row: iiwa14, N=32, B=512, the reference's flags).
 # "all": the whole matrix oracle/gen_golden.py uses to mint tests/golden/ (BASELINE.json configs + the bench shape; ~15 min on 6 jobs).
+# "pin": the IEEE builds tools/pin_cost_gradient.py and tools/pin_whole_solve.py compare the oracle with (15 horizons / plants).
+if [ "${1:-}" = pin ]; then
+  JOBS=${GREF_JOBS:-6}
+  { for n in 3 4 6 8 9 10 11 12 16 32 64; do echo "iiwa14 $n 1,16 ieee"; done; echo "iiwa14 128 8 ieee"; for n in 8 16 32; do echo "indy7 $n 16 ieee"; done; } | xargs -P "$JOBS" -L 1 "$0"
+  exit 0
+fi
 if [ "${1:-}" != all ]; then
   build_one iiwa14 32 16,128,512 fast
   exit 0

@@ -48,7 +48,7 @@ static void stage_kkt(int N, int B, const float* xu, const float* xs, const floa
                         float* Rk = R_ + ((size_t)b * N + k) * NU * NU;
                         float* rk = r + ((size_t)b * N + k) * NU;
                         Items<P>::template cost_grad_hess<true>(xux, ref + (size_t)b * 6 * N + 6 * k, cs, [&](int e, float v) { Qk[e] = v; }, [&](int e, float v) { qk[e] = v; },
-                                                                [&](int e, float v) { Rk[e] = v; }, [&](int e, float v) { rk[e] = v; });
+                                                                [&](int e, float v) { Rk[e] = v; }, [&](int e, float v) { rk[e] = v; }, false, Items<P>::pos_form_b_for(N));
                         if (k == N - 2) {
                                 float* Qn = Qk + NX * NX;
                                 float* qn = qk + NX;

@@ -110,7 +110,10 @@ def test_whole_solve_n8_matches_reference(oracle_built, mode):
             if variant == "a_":  # second solve without reset: lambda / rho persistence (bsqp.cuh:81-87,189)
                 o2 = s.solve(o["XU"], G[base + "xs"], G[base + "ref"], float(G[base + "dt"]))
                 assert np.array_equal(o2["pcg_iters"], G[base + "b_pcg_iters"])
-                assert rel_err(o2["XU"], G[base + "b_XU"]) < (1e-6 if mode == "ieee" else 1e-4)
+                if mode == "ieee":
+                    assert n_mismatch(o2["XU"], G[base + "b_XU"]) == 0
+                else:
+                    assert rel_err(o2["XU"], G[base + "b_XU"]) < 1e-4
             sim = s
             sim.set_batch("f_ext", G[base + "sim_fext"])
             if variant == "d_":
@@ -119,7 +122,7 @@ def test_whole_solve_n8_matches_reference(oracle_built, mode):
 
 
 def test_whole_solve_n32_default_params(oracle_built):
-    """N=32, one SQP iteration, tolerance-terminated PCG: integer outcomes equal, trajectories within 1e-4 (IEEE build)."""
+    """N=32, one SQP iteration, tolerance-terminated PCG: integer outcomes equal, every trajectory bit-for-bit (IEEE build)."""
     G = load_golden("iiwa14", 32, "ieee")
     be = Backend("oracle", "iiwa14", 32)
     base = "solve_B16_"
@@ -128,9 +131,8 @@ def test_whole_solve_n32_default_params(oracle_built):
     assert np.array_equal(o["pcg_iters"], G[base + "d_pcg_iters"])
     assert np.array_equal(o["ls_step_size"], G[base + "d_ls_step_size"])
     assert np.array_equal(o["sqp_iters"], G[base + "d_sqp_iters"]) and np.array_equal(o["kkt_converged"], G[base + "d_kkt_converged"])
-    assert rel_err(o["XU"], G[base + "d_XU"]) < 1e-4
-    assert rel_err(o["initial_merit"], G[base + "d_initial_merit"]) < 1e-6
-    assert int((np.abs(o["XU"] - G[base + "d_XU"]).max(axis=1) == 0).sum()) >= 8  # most solves reproduce bit-for-bit
+    assert n_mismatch(o["XU"], G[base + "d_XU"]) == 0
+    assert rel_err(o["initial_merit"], G[base + "d_initial_merit"]) < 1e-6  # the reference sums the knots with unordered atomics
 
 
 def test_reference_is_reproducible_in_fixtures():
