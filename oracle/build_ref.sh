@@ -3,7 +3,7 @@
 # they lie) into oracle/_ref/libgref_<plant>_N<N>_<fast|ieee>.so through oracle/ref_harness.cu.
 #   fast = the reference's own flags (CMakeLists.txt:20-22: -O3 -use_fast_math -DNDEBUG), arch swapped to sm_100
 #   ieee = same without -use_fast_math (isolates fast-math noise from algorithmic parity)
-# Usage: oracle/build_ref.sh                 the library bench.py times (iiwa14 N=32)
+# Usage: oracle/build_ref.sh                 the two libraries the GPU box uses: bench.py's (iiwa14 N=32, fast) and the live parity test's (ieee)
 #        oracle/build_ref.sh all             every library oracle/gen_golden.py needs, in parallel
 #        oracle/build_ref.sh pin             the IEEE builds the tools/pin_*.py comparisons use
 #        oracle/build_ref.sh plant N batches mode [...]
@@ -36,7 +36,8 @@ if [ $# -ge 4 ]; then
   exit 0
 fi
 
-# no arguments: the one library the GPU box needs at run time (bench.py's reference_gpu row: iiwa14, N=32, B=512, the reference's flags).
+# no arguments: the libraries the GPU box needs at run time (bench.py's reference_gpu row: iiwa14, N=32, B=512, the reference's flags; and
+# the IEEE build tests/test_gpu_reference_live.py compares the CUDA path with).
 # "all": the whole matrix oracle/gen_golden.py uses to mint tests/golden/ (BASELINE.json configs + the bench shape; ~15 min on 6 jobs).
 # "pin": the IEEE builds tools/pin_cost_gradient.py and tools/pin_whole_solve.py compare the oracle with (15 horizons / plants).
 if [ "${1:-}" = pin ]; then
@@ -45,7 +46,10 @@ if [ "${1:-}" = pin ]; then
   exit 0
 fi
 if [ "${1:-}" != all ]; then
-  build_one iiwa14 32 16,128,512 fast
+  # bench.py's reference_gpu row (the reference's own flags) and the live parity test's IEEE build, side by side
+  build_one iiwa14 32 16,128,512 fast &
+  build_one iiwa14 32 16,128 ieee &
+  wait
   exit 0
 fi
 JOBS=${GREF_JOBS:-6}
