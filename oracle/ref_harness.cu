@@ -18,6 +18,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include <algorithm>
@@ -307,7 +308,17 @@ int stage_merit(const float* xu, const float* dz, const float* xs, const float* 
         in.d_x_s_batch = dxs.p;
         in.d_reference_traj_batch = dref.p;
         in.d_GRiD_mem = nullptr;
-        if (num_alphas == 1)
+        if (getenv("GREF_MERIT_EXTRA_SMEM")) {
+                // The reference's own launcher (merit.cuh:110-141) requests too little dynamic shared memory for indy7 (and for iiwa14 at
+                // N = 128): the kernel writes past it and faults on B200.  With this switch the harness launches the SAME, unmodified kernel
+                // with the launcher's grid and arguments but with extra shared memory, so that the stage can be compared at all.
+                const int    na = num_alphas == 1 ? 1 : NUM_ALPHAS;
+                const size_t smem = getComputeMeritBatchedSMemSize<float>() + (size_t)atoi(getenv("GREF_MERIT_EXTRA_SMEM"));
+                CK(cudaFuncSetAttribute(computeMeritBatchedKernel<float, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(cudaMemset(dm.p, 0, sizeof(float) * B * na));
+                computeMeritBatchedKernel<float, B><<<dim3(KNOT_POINTS, B, na), dim3(grid::SUGGESTED_THREADS), smem>>>(
+                    dm.p, ddz.p, dxu.p, in.d_x_s_batch, in.d_reference_traj_batch, grid_mem(), dmu.p, dfe.p, in.timestep, cost7[0], cost7[1], cost7[2], cost7[3], cost7[4], cost7[5], cost7[6]);
+        } else if (num_alphas == 1)
                 computeMeritBatched<float, B, 1>(dm.p, ddz.p, dxu.p, dfe.p, in, dmu.p, grid_mem(), cost7[0], cost7[1], cost7[2], cost7[3], cost7[4], cost7[5], cost7[6]);
         else
                 computeMeritBatched<float, B, NUM_ALPHAS>(dm.p, ddz.p, dxu.p, dfe.p, in, dmu.p, grid_mem(), cost7[0], cost7[1], cost7[2], cost7[3], cost7[4], cost7[5], cost7[6]);

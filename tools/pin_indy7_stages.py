@@ -43,6 +43,16 @@ for adapt in (1, 0):
     lsr = ref.stage_linesearch(B, xu, dzo[0], merit8, mi, rho, np.ones(B, np.float32), adapt)
     lso = orc.stage_linesearch(B, xu, dzo[0], merit8, mi, rho, np.ones(B, np.float32), adapt)
     print(f"linesearch adapt={adapt}", {k: nm(lsr[k], lso[k]) for k in lso})
+# merit: the unmodified kernel launched by the harness with enough dynamic shared memory (GREF_MERIT_EXTRA_SMEM, see oracle/ref_harness.cu);
+# the reference accumulates the knots with atomics in arbitrary order, so the comparison is to float rounding of a 32-term sum
+import os
+
+os.environ["GREF_MERIT_EXTRA_SMEM"] = "4096"
+mu = np.full(B, 10.0, np.float32)
+for na in (1, 8):
+    mr = ref.stage_merit(B, xu, dzo[0], w["xs"], w["ref"], mu, fext, w["dt"], p, na)
+    mo = orc.stage_merit(B, xu, dzo[0], w["xs"], w["ref"], mu, fext, w["dt"], p, na)
+    print(f"merit x{na}: max rel diff {float(np.max(np.abs(mr - mo) / np.abs(mo))):.2e}, bit-identical entries {int((mr.view(np.uint32) == mo.view(np.uint32)).sum())}/{mr.size}")
 d_r, d_o = ref.dyn_dump(xu[:, :12], xu[:, 12:18], fext), orc.dyn_dump(xu[:, :12], xu[:, 12:18], fext)
 # the pose's orientation part (roll, pitch, yaw and its Jacobian rows) never enters the solver (iiwa14_plant.cuh:313-319) and is not restated
 ee_r, ee_o = d_r["ee"][:, :3], d_o["ee"][:, :3]
