@@ -48,9 +48,13 @@ fi
 if [ "${1:-}" != all ]; then
   # bench.py's reference_gpu row (the reference's own flags) and the live parity test's IEEE build, side by side
   build_one iiwa14 32 16,128,512 fast &
+  p1=$!
   build_one iiwa14 32 16,128 ieee &
-  wait
-  exit 0
+  p2=$!
+  rc=0
+  wait $p1 || rc=1
+  wait $p2 || rc=1
+  exit $rc
 fi
 JOBS=${GREF_JOBS:-6}
 cat <<LIST | xargs -P "$JOBS" -L 1 "$0"
