@@ -283,3 +283,44 @@ def test_randomized_whole_solves_bit_exact(backends):
             assert np.array_equal(rg[k], ro[k]), f"{tag} {k}"
         for k in ("XU", "ls_step_size", "ls_min_merit", "final_merit", "initial_merit"):
             assert n_mismatch(rg[k], ro[k]) == 0, f"{tag} {k}"
+
+
+def test_cabi_error_paths_and_concurrent_solvers():
+    """C-ABI behaviour on a GPU box: unsupported horizons and bad arguments return error codes with a message (the reference aborts or ignores
+    CUDA errors, cuda.cuh:7-19); two solvers driven from two host threads on their own streams give the same bits as one after the other."""
+    import ctypes as C
+    import threading
+
+    from gato_b200 import native
+
+    lib = native.load()
+    h = C.c_void_p()
+    prm = native.make_params(dict(DEFAULT_SOLVER_PARAMS, dt=0.01))
+    assert lib.gato_create(C.byref(h), 1, 400, 4, 0, None, C.byref(prm)) == -3  # GATO_ERR_UNSUPPORTED: (N+2)*nx > 4096
+    assert b"knot_points too large" in lib.gato_last_error(None)
+    assert lib.gato_create(C.byref(h), 1, 32, 4, 99, None, C.byref(prm)) == -2  # GATO_ERR_CUDA: no such device
+    assert lib.gato_create(C.byref(h), 1, 32, 4, 0, None, C.byref(prm)) == 0
+    assert lib.gato_solve(h, None, None, None, C.c_float(0.01), None) == -1  # GATO_ERR_ARG
+    assert lib.gato_reset(h, 7) == -1 and b"unknown reset field" in lib.gato_last_error(h)
+    out = native.GatoMpcOut()
+    x = np.zeros(14, np.float32)
+    ref = np.zeros(6 * 32, np.float32)
+    assert lib.gato_mpc_step(h, x, ref, None, None, C.c_float(0.0), C.c_float(0.01), 0, C.byref(out), None) == -1  # no warm start set
+    assert b"gato_mpc_set_warm_start" in lib.gato_last_error(h)
+    lib.gato_destroy(h)
+
+    w = make_config(2, B=64)
+    serial = [native.Solver(w["plant"], w["N"], 64, w["params"], device=0).solve(w["xu"], w["xs"], w["ref"], w["dt"]) for _ in range(2)]
+    results = [None, None]
+
+    def run(i):
+        s = native.Solver(w["plant"], w["N"], 64, w["params"], device=0)
+        for _ in range(3):
+            s.reset("dual"), s.reset("rho")
+            results[i] = s.solve(w["xu"], w["xs"], w["ref"], w["dt"])
+
+    ts = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for i in range(2):
+        assert n_mismatch(results[i]["XU"], serial[0]["XU"]) == 0 and np.array_equal(results[i]["pcg_iters"], serial[1]["pcg_iters"])
