@@ -28,6 +28,9 @@ def run(kind, w, steps, B):
     fig = figure8(dt).reshape(-1, 6)
     off = (w["xs"] - w["xs"].mean(0, keepdims=True)).astype(np.float32)
     x = np.zeros(nx, np.float32)
+    # the simulated plant saturates its actuators at the robot's torque limits (iiwa14_plant.cuh:57-70), as the real one does; without it
+    # this synthetic scenario (start pose 0.8 m away from the figure-8, cheap control) runs away within ~60 steps
+    u_max = np.array([320.0, 320.0, 176.0, 176.0, 110.0, 40.0, 40.0], np.float32)
     true_hyp = B // 2
     XU = np.zeros((B, traj), np.float32)
     lat, dev_ms, best_hist = [], [], []
@@ -41,7 +44,7 @@ def run(kind, w, steps, B):
         r, _, _ = host_mpc_step(s, XU, x, fig[:N].reshape(-1), None, None, 0.0, dt, reset_rho=False, offsets=off)
         xu_best = XU[0].copy()
     for k in range(1, steps + 1):
-        x_last, u_last = x.copy(), xu_best[nx:nx + nu].copy()
+        x_last, u_last = x.copy(), np.clip(xu_best[nx:nx + nu], -u_max, u_max).astype(np.float32)
         x = s.sim_forward(x_last, u_last, dt)[true_hyp].copy()
         ref_w = fig[k % 500:k % 500 + N].reshape(-1)
         t0 = time.perf_counter()
@@ -70,6 +73,7 @@ def main():
         res[kind] = (xu, best)
         out[kind] = {"step_ms_p50": float(np.median(lat)), "step_ms_p95": float(np.percentile(lat, 95)), "device_ms_p50": float(np.median(dev_ms)),
                      "solves_per_s": a.batch / (np.median(lat) * 1e-3)}
+    out["finite"] = bool(np.isfinite(res["host"][0]).all() and np.isfinite(res["device"][0]).all())
     out["identical_trajectories"] = bool(np.array_equal(res["host"][0], res["device"][0]) and res["host"][1] == res["device"][1])
     out["speedup_step_p50"] = out["host"]["step_ms_p50"] / out["device"]["step_ms_p50"]
     print(json.dumps(out))
