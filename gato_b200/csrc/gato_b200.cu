@@ -661,7 +661,8 @@ __global__ void k_mpc_score(int B, int nx, const float* __restrict__ xnext, cons
                 }
                 const double e = sqrt(res);
                 err[b] = e;
-                if (bi < 0 || e < bv) bv = e, bi = b;  // ascending b per thread: strict < keeps the first minimum
+                // np.argmin: the first minimum; a NaN counts as smaller than everything (the first NaN wins).  ascending b per thread.
+                if (bi < 0 || (bv == bv && (e != e || e < bv))) bv = e, bi = b;
         }
         s_val[threadIdx.x] = bv;
         s_idx[threadIdx.x] = bi;
@@ -671,9 +672,17 @@ __global__ void k_mpc_score(int B, int nx, const float* __restrict__ xnext, cons
                 int    id = -1;
                 for (int t = 0; t < (int)blockDim.x; t++) {
                         if (s_idx[t] < 0) continue;
-                        if (id < 0 || s_val[t] < v || (s_val[t] == v && s_idx[t] < id)) v = s_val[t], id = s_idx[t];
+                        const double x = s_val[t];
+                        const bool   xn = x != x, vn = v != v;
+                        bool         take;
+                        if (id < 0)
+                                take = true;
+                        else if (xn || vn)
+                                take = xn && (!vn || s_idx[t] < id);  // NaN beats numbers; among NaNs the smallest index
+                        else
+                                take = x < v || (x == v && s_idx[t] < id);
+                        if (take) v = x, id = s_idx[t];
                 }
-                // NaN errors: np.argmin returns the first NaN; keep it simple and deterministic: NaNs never win, id stays >= 0 if any finite
                 best[0] = id < 0 ? 0 : id;
         }
 }

@@ -92,7 +92,7 @@ int gato_get_merits(gato_solver* s, float* h_final /*[B] or NULL*/, float* h_ini
  *   x_s[b] = x_curr (+ x_offset[b] if set), ref[b] = ref_window, XU[b][0:nx] = x_s[b]          (mpc_controller.py:238-242)
  *   reset_rho (optional, :245), solve (:248),
  *   x_next[b] = sim_forward(x_last, u_last, sim_dt) under hypothesis b's f_ext; err[b] = ||x_next[b] - x_curr||_2 in float64
- *   with numpy's summation order; best = first argmin (:298-303)                                   (skipped when h_x_last == NULL: best = 0)
+ *   with numpy's summation order; best = np.argmin (first minimum; the first NaN wins) (:298-303)   (skipped when h_x_last == NULL: best = 0)
  *   XU[:] = XU[best]  (:252-253) -- the batch of warm starts stays resident on the device between steps.
  * The warm-start batch is solver-owned: seed it with gato_mpc_set_warm_start before the first step. */
 typedef struct gato_mpc_out {

@@ -93,3 +93,23 @@ def test_device_mpc_state_offsets_match_host_composition():
     r_h, b_h, e_h = host_mpc_step(host, XU_h, x, ref_w, x, np.zeros(nu, np.float32), dt, dt, offsets=off)
     assert r_dev["best_id"] == b_h and np.array_equal(r_dev["errors"], e_h)
     assert np.array_equal(r_dev["XU_best"], XU_h[0])
+
+
+def test_device_mpc_scoring_follows_numpy_argmin_with_nan():
+    """np.argmin returns the first NaN if there is one (mpc_controller.py:301): a hypothesis whose wrench is NaN must win on the device too."""
+    p, dt, fig, fext, dev, host, mk = _setup("iiwa14", 8, 16, 21)
+    B, N = 16, 8
+    nx, nu, traj = dev.d["nx"], dev.d["nu"], dev.d["traj"]
+    fe = fext.copy()
+    fe[5, 2] = np.nan
+    fe[11, 0] = np.nan
+    dev.set_batch("f_ext", fe), host.set_batch("f_ext", fe)
+    x = np.zeros(nx, np.float32)
+    XU_h = np.zeros((B, traj), np.float32)
+    dev.reset("dual"), host.reset("dual")
+    dev.mpc_set_warm_start(XU_h[0])
+    ref_w = fig[:N].reshape(-1)
+    r_dev = dev.mpc_step(x, ref_w, x, np.zeros(nu, np.float32), dt, dt, reset_rho=True)
+    r_h, b_h, e_h = host_mpc_step(host, XU_h, x, ref_w, x, np.zeros(nu, np.float32), dt, dt)
+    assert b_h == 5 and r_dev["best_id"] == b_h
+    assert np.array_equal(np.isnan(r_dev["errors"]), np.isnan(e_h)) and np.array_equal(r_dev["errors"][~np.isnan(e_h)], e_h[~np.isnan(e_h)])
