@@ -17,7 +17,12 @@ void enqueue_pcg<GATO_TU_PLANT>(const Ctx& c, int rpt, int threads, size_t smem,
 {
         using P = GATO_TU_PLANT;
         switch (rpt) {
-                case 0: k_pcg<P><<<c.B, threads, smem, st>>>(c); break;
+                case 0:
+                        if (threads <= 480)
+                                k_pcg<P, 480><<<c.B, threads, smem, st>>>(c);
+                        else
+                                k_pcg<P, 512><<<c.B, threads, smem, st>>>(c);
+                        break;
                 case 1: k_pcg_stream<P, 1><<<c.B, 1024, smem, st>>>(c); break;
                 case 2: k_pcg_stream<P, 2><<<c.B, 1024, smem, st>>>(c); break;
                 case 3: k_pcg_stream<P, 3><<<c.B, 1024, smem, st>>>(c); break;
@@ -31,7 +36,10 @@ cudaError_t configure_linalg<GATO_TU_PLANT>(int rpt, size_t smem_pcg, size_t sme
         cudaError_t e = cudaFuncSetAttribute(k_schur<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur);
         if (e != cudaSuccess) return e;
         switch (rpt) {
-                case 0: return cudaFuncSetAttribute(k_pcg<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pcg);
+                case 0:
+                        e = cudaFuncSetAttribute(k_pcg<P, 480>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pcg);
+                        if (e != cudaSuccess) return e;
+                        return cudaFuncSetAttribute(k_pcg<P, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pcg);
                 case 1: return cudaFuncSetAttribute(k_pcg_stream<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pcg);
                 case 2: return cudaFuncSetAttribute(k_pcg_stream<P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pcg);
                 case 3: return cudaFuncSetAttribute(k_pcg_stream<P, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pcg);

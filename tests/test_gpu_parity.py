@@ -76,7 +76,7 @@ def test_every_stage_bit_exact_vs_oracle(backends, plant, N, cfg, B):
             assert n_mismatch(lsg[k], lso[k]) == 0, f"line search {k}"
 
 
-@pytest.mark.parametrize("plant,N,cfg,B", [("iiwa14", 8, 1, 1), ("iiwa14", 32, 2, 16), ("indy7", 32, 3, 16), ("iiwa14", 32, 5, 16), ("iiwa14", 128, 4, 4), ("iiwa14", 9, 2, 5), ("indy7", 33, 3, 3)])
+@pytest.mark.parametrize("plant,N,cfg,B", [("iiwa14", 8, 1, 1), ("iiwa14", 32, 2, 16), ("indy7", 32, 3, 16), ("iiwa14", 32, 5, 16), ("iiwa14", 128, 4, 4), ("iiwa14", 9, 2, 5), ("indy7", 33, 3, 3), ("iiwa14", 34, 2, 3), ("indy7", 40, 3, 2)])
 def test_whole_solve_bit_exact_vs_oracle(backends, plant, N, cfg, B):
     o, g = backends(plant, N)
     w = make_config(cfg, B=B, N=N)
