@@ -294,16 +294,19 @@ __global__ void __launch_bounds__(32) k_kkt_fine(Ctx c)
 // k_merit_ls: one CTA per solve, thread per (alpha, knot) — computeMeritBatchedKernel + lineSearchAndUpdateBatchedKernel
 // NA = 8: merit at z + 2^-a dz for a = 0..7, then the line search.  NA = 1: merit at z (initial / final merit).
 // =====================================================================================================
-template<class P, int NA>
-__global__ void __launch_bounds__(NA == 1 ? 128 : 256, NA == 1 ? 1 : GATO_MERIT_MIN_BLOCKS) k_merit_ls(Ctx c)
+// SPLIT (small batches, where a launch lasts as long as one thread's instruction stream): two threads per (alpha, knot) -- one evaluates the
+// forward dynamics and the defect, the other the tracking cost -- combined as fmaf(mu, defect, cost) exactly like the single-thread version.
+template<class P, int NA, bool SPLIT = false>
+__global__ void __launch_bounds__(SPLIT ? 512 : (NA == 1 ? 128 : 256), (NA == 1 || SPLIT) ? 1 : GATO_MERIT_MIN_BLOCKS) k_merit_ls(Ctx c)
 {
         constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ;
         if (NA > 1 && stopped_before(c, c.it + 1)) return;  // the iteration that meets the test skips merit + line search (bsqp.cuh:165)
-        extern __shared__ float smf[];                       // [NA][N] per-knot merits, then NA sums
+        extern __shared__ float smf[];                       // [NA][N] per-knot merits, NA sums, (SPLIT: [NA][N] cost halves)
         const int               N = c.N, b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
         const int               traj = (NX + NU) * N - NU;
         float*                  mk = smf;
         float*                  msum = smf + NA * N;
+        float*                  mcost = msum + NA;
         const float*            xu = c.xu + (size_t)b * traj;
         const float*            dz = c.dz + (size_t)b * traj;
         if (c.flags & F_MERIT) {
@@ -311,7 +314,8 @@ __global__ void __launch_bounds__(NA == 1 ? 128 : 256, NA == 1 ? 1 : GATO_MERIT_
                 const bool  zero_dz = (c.flags & F_ZERO_DZ) != 0;
                 float       fext[6];
                 sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * b + ic]; });
-                for (int w = tid; w < NA * N; w += T) {
+                for (int w0 = tid; w0 < (SPLIT ? 2 : 1) * NA * N; w0 += T) {
+                        const int   half = SPLIT ? w0 / (NA * N) : 0, w = SPLIT ? w0 % (NA * N) : w0;
                         const int   a = w / N, k = w % N;
                         const float alpha = (float)(1.0 / (double)(1 << a));
                         float       ref3[3];
@@ -324,7 +328,10 @@ __global__ void __launch_bounds__(NA == 1 ? 128 : 256, NA == 1 ? 1 : GATO_MERIT_
                                         sfor<0, 2 * NX + NU>([&](auto ic) { xux[ic] = xk[ic]; });
                                 else
                                         sfor<0, 2 * NX + NU>([&](auto ic) { xux[ic] = fmaf(alpha, dk[ic], xk[ic]); });
-                                m = Items<P>::merit_mid(xux, ref3, mu, fext, c.dt, c.cs);
+                                if constexpr (SPLIT)
+                                        m = half == 0 ? Items<P>::merit_mid_cons(xux, fext, c.dt) : Items<P>::template tracking_cost<false>(xux, ref3, c.cs);
+                                else
+                                        m = Items<P>::merit_mid(xux, ref3, mu, fext, c.dt, c.cs);
                         } else {
                                 float e0[NX];
                                 if (zero_dz) {
@@ -334,11 +341,21 @@ __global__ void __launch_bounds__(NA == 1 ? 128 : 256, NA == 1 ? 1 : GATO_MERIT_
                                         sfor<0, NX>([&](auto ic) { xux[ic] = fmaf(alpha, dk[ic], xk[ic]); });
                                         sfor<0, NX>([&](auto ic) { e0[ic] = fabsf(fmaf(alpha, dz[ic], xu[ic]) - c.xs[(size_t)b * NX + ic]); });
                                 }
-                                m = Items<P>::merit_last(xux, ref3, mu, e0, c.cs);
+                                if constexpr (SPLIT)
+                                        m = half == 0 ? Items<P>::merit_last_cons(e0) : Items<P>::template tracking_cost<true>(xux, ref3, c.cs);
+                                else
+                                        m = Items<P>::merit_last(xux, ref3, mu, e0, c.cs);
                         }
-                        mk[a * N + k] = m;
+                        if (SPLIT && half == 1)
+                                mcost[a * N + k] = m;
+                        else
+                                mk[a * N + k] = m;
                 }
                 __syncthreads();
+                if constexpr (SPLIT) {
+                        for (int w = tid; w < NA * N; w += T) mk[w] = fmaf(mu, mk[w], mcost[w]);
+                        __syncthreads();
+                }
                 if (tid < NA) {
                         // the reference sums the knots with unordered float atomics (merit.cuh:88-91); here: ascending k
                         float s = 0.0f;

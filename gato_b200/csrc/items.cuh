@@ -305,6 +305,25 @@ struct Items {
                 const float cons = tree_reduce<NX>(err);
                 return fmaf(mu, cons, cost);
         }
+        // the two halves of merit_mid for the split kernel (small batches): merit = fmaf(mu, merit_mid_cons, tracking_cost<false>)
+        static GATO_HD float merit_mid_cons(const float* xux, const float* fext, float dt)
+        {
+                float qdd[NQ], qn[NQ], qdn[NQ], err[NX];
+                R::forward_dynamics(xux, xux + NQ, xux + NX, fext, qdd);
+                R::integrate(xux, xux + NQ, qdd, dt, qn, qdn);
+                sfor<0, NQ>([&](auto ic) {
+                        constexpr int i = ic;
+                        err[i] = fabsf(xux[NX + NU + i] - qn[i]);
+                        err[i + NQ] = fabsf(xux[NX + NU + NQ + i] - qdn[i]);
+                });
+                return tree_reduce<NX>(err);
+        }
+        static GATO_HD float merit_last_cons(const float* x0err)
+        {
+                float err[NX];
+                sfor<0, NX>([&](auto ic) { err[ic] = x0err[ic]; });
+                return tree_reduce<NX>(err);
+        }
         static GATO_HD float merit_last(const float* x, const float* ref3, float mu, const float* x0err, const Costs& cs)
         {
                 const float cost = tracking_cost<true>(x, ref3, cs);

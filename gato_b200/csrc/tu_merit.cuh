@@ -14,6 +14,12 @@ template<>
 void enqueue_merit<GATO_TU_PLANT>(const Ctx& c, int na, cudaStream_t st)
 {
         const size_t smem = sizeof(float) * (size_t)(na * c.N + na);
+        // small batches (one CTA per SM at most) with room for two threads per (alpha, knot) in one block: the split kernel
+        if (na == kNumAlphas && c.B <= 148 && 2 * na * c.N <= 512) {
+                const int threads = (2 * na * c.N + 31) / 32 * 32;
+                k_merit_ls<GATO_TU_PLANT, kNumAlphas, true><<<c.B, threads, smem + sizeof(float) * (size_t)(na * c.N), st>>>(c);
+                return;
+        }
         if (na == 1)
                 k_merit_ls<GATO_TU_PLANT, 1><<<c.B, merit_threads(1, c.N), smem, st>>>(c);
         else
