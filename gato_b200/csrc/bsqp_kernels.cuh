@@ -99,14 +99,22 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
                 sfor<0, 2 * NX + NU>([&](auto ic) { xux[ic] = src[ic]; });
         }
         // write staged rows [row0, row0+count) of every selected item to dst[(b*N + knot + koff)*stride + off + e]
-        auto flush = [&](float* dst, int row0, int count, int stride, int off, int koff, int which /*0 non-terminal, 1 terminal, 2 all*/) {
-                const int nvalid = min(32, total - item0);
-                for (int i = 0; i < nvalid; i++) {
-                        const int  it_ = item0 + i, bi = it_ / per, ki = it_ % per;
-                        const bool ti = (kind == 0) && (ki == c.N - 1);
+        // rowbase[i] = global knot index (b * N + k) of the warp's i-th item, bit 30 set for the terminal item: written once, so that the
+        // flushes below need no integer divisions
+        __shared__ int rowbase[32];
+        rowbase[lane] = (b * c.N + k) | (term ? (1 << 30) : 0);
+        __syncwarp();
+        // write staged rows [row0, row0+COUNT) of every selected item to dst[(b*N + knot + koff)*stride + off + e]; the (item, element) pairs are
+        // flattened over the lanes so that every store instruction is full and consecutive lanes write consecutive addresses
+        auto flush = [&](auto count_c, float* dst, int row0, int stride, int off, int koff, int which /*0 non-terminal, 1 terminal, 2 all*/) {
+                constexpr int COUNT = decltype(count_c)::value;
+                const int     nvalid = min(32, total - item0);
+                for (int f = lane; f < nvalid * COUNT; f += 32) {
+                        const int  i = f / COUNT, e = f - i * COUNT;
+                        const int  rb = rowbase[i];
+                        const bool ti = (rb >> 30) & 1;
                         if ((which == 0 && ti) || (which == 1 && !ti)) continue;
-                        float* d = dst + ((size_t)bi * c.N + ki + koff) * stride + off;
-                        for (int e = lane; e < count; e += 32) d[e] = stage[(row0 + e) * ST + i];
+                        dst[((size_t)(rb & ~(1 << 30)) + koff) * stride + off + e] = stage[(row0 + e) * ST + i];
                 }
         };
         if (kind == 0) {
@@ -137,8 +145,8 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
                 {  // Q and R: expand the staged entries, zeros elsewhere
                         const int nvalid = min(32, total - item0);
                         for (int i = 0; i < nvalid; i++) {
-                                const int  it_ = item0 + i, bi = it_ / per, ki = it_ % per;
-                                float*     dQ = c.Q + ((size_t)bi * c.N + ki) * NX * NX;
+                                const int  rb = rowbase[i] & ~(1 << 30), ki = (rowbase[i] >> 30) & 1 ? c.N - 1 : 0;
+                                float*     dQ = c.Q + (size_t)rb * NX * NX;
                                 for (int e = lane; e < NX * NX; e += 32) {
                                         const int r_ = e / NX, c_ = e % NX;
                                         float     v = 0.0f;
@@ -149,14 +157,14 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
                                         dQ[e] = v;
                                 }
                                 if (ki != c.N - 1) {
-                                        float* dR = c.R + ((size_t)bi * c.N + ki) * NU * NU;
+                                        float* dR = c.R + (size_t)rb * NU * NU;
                                         for (int e = lane; e < NU * NU; e += 32) dR[e] = (e / NU == e % NU) ? stage[(rR + e / NU) * ST + i] : 0.0f;
                                 }
                         }
                 }
-                flush(c.q, rq, NX, NX, 0, 0, 2);
-                flush(c.r, rr, NU, NU, 0, 0, 0);
-                flush(c.c, rc0, NX, NX, 0, -(c.N - 1), 1);
+                flush(std::integral_constant<int, NX>{}, c.q, rq, NX, 0, 0, 2);
+                flush(std::integral_constant<int, NU>{}, c.r, rr, NU, 0, 0, 0);
+                flush(std::integral_constant<int, NX>{}, c.c, rc0, NX, 0, -(c.N - 1), 1);
         } else {
                 float fext[6];
                 sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * b + ic]; });
@@ -165,14 +173,14 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
                         Items<P>::template linearize_half_rolled<0>(
                             xux, fext, c.dt, [&](int e, float v) { stage[(rA + e) * ST + lane] = v; }, [&](int, float) {}, [&](int e, float v) { stage[(rX + e) * ST + lane] = v; });
                         __syncwarp();
-                        flush(c.A, rA, NX * NQ, NX * NX, 0, 0, 2);
-                        flush(c.c, rX, NX, NX, 0, 1, 2);
+                        flush(std::integral_constant<int, NX * NQ>{}, c.A, rA, NX * NX, 0, 0, 2);
+                        flush(std::integral_constant<int, NX>{}, c.c, rX, NX, 0, 1, 2);
                 } else {
                         Items<P>::template linearize_half_rolled<1>(
                             xux, fext, c.dt, [&](int e, float v) { stage[(rA + e - NX * NQ) * ST + lane] = v; }, [&](int e, float v) { stage[(rX + e) * ST + lane] = v; }, [&](int, float) {});
                         __syncwarp();
-                        flush(c.A, rA, NX * NQ, NX * NX, NX * NQ, 0, 2);
-                        flush(c.Bm, rX, NX * NU, NX * NU, 0, 0, 2);
+                        flush(std::integral_constant<int, NX * NQ>{}, c.A, rA, NX * NX, NX * NQ, 0, 2);
+                        flush(std::integral_constant<int, NX * NU>{}, c.Bm, rX, NX * NU, 0, 0, 2);
                 }
         }
 }
@@ -209,14 +217,22 @@ __global__ void __launch_bounds__(32) k_kkt_fine(Ctx c)
                 const float* src = c.xu + (size_t)b * traj + (size_t)ks * (NX + NU);
                 sfor<0, 2 * NX + NU>([&](auto ic) { xux[ic] = src[ic]; });
         }
-        auto flush = [&](float* dst, int row0, int count, int stride, int off, int koff, int which) {
-                const int nvalid = min(32, total - item0);
-                for (int i = 0; i < nvalid; i++) {
-                        const int  it_ = item0 + i, bi = it_ / per, ki = it_ % per;
-                        const bool ti = (kind == 0) && (ki == c.N - 1);
+        // rowbase[i] = global knot index (b * N + k) of the warp's i-th item, bit 30 set for the terminal item: written once, so that the
+        // flushes below need no integer divisions
+        __shared__ int rowbase[32];
+        rowbase[lane] = (b * c.N + k) | (term ? (1 << 30) : 0);
+        __syncwarp();
+        // write staged rows [row0, row0+COUNT) of every selected item to dst[(b*N + knot + koff)*stride + off + e]; the (item, element) pairs are
+        // flattened over the lanes so that every store instruction is full and consecutive lanes write consecutive addresses
+        auto flush = [&](auto count_c, float* dst, int row0, int stride, int off, int koff, int which /*0 non-terminal, 1 terminal, 2 all*/) {
+                constexpr int COUNT = decltype(count_c)::value;
+                const int     nvalid = min(32, total - item0);
+                for (int f = lane; f < nvalid * COUNT; f += 32) {
+                        const int  i = f / COUNT, e = f - i * COUNT;
+                        const int  rb = rowbase[i];
+                        const bool ti = (rb >> 30) & 1;
                         if ((which == 0 && ti) || (which == 1 && !ti)) continue;
-                        float* d = dst + ((size_t)bi * c.N + ki + koff) * stride + off;
-                        for (int e = lane; e < count; e += 32) d[e] = stage[(row0 + e) * ST + i];
+                        dst[((size_t)(rb & ~(1 << 30)) + koff) * stride + off + e] = stage[(row0 + e) * ST + i];
                 }
         };
         if (kind == 0) {
@@ -245,8 +261,8 @@ __global__ void __launch_bounds__(32) k_kkt_fine(Ctx c)
                 {
                         const int nvalid = min(32, total - item0);
                         for (int i = 0; i < nvalid; i++) {
-                                const int it_ = item0 + i, bi = it_ / per, ki = it_ % per;
-                                float*    dQ = c.Q + ((size_t)bi * c.N + ki) * NX * NX;
+                                const int  rb = rowbase[i] & ~(1 << 30), ki = (rowbase[i] >> 30) & 1 ? c.N - 1 : 0;
+                                float*     dQ = c.Q + (size_t)rb * NX * NX;
                                 for (int e = lane; e < NX * NX; e += 32) {
                                         const int r_ = e / NX, c_ = e % NX;
                                         float     v = 0.0f;
@@ -257,14 +273,14 @@ __global__ void __launch_bounds__(32) k_kkt_fine(Ctx c)
                                         dQ[e] = v;
                                 }
                                 if (ki != c.N - 1) {
-                                        float* dR = c.R + ((size_t)bi * c.N + ki) * NU * NU;
+                                        float* dR = c.R + (size_t)rb * NU * NU;
                                         for (int e = lane; e < NU * NU; e += 32) dR[e] = (e / NU == e % NU) ? stage[(rR + e / NU) * ST + i] : 0.0f;
                                 }
                         }
                 }
-                flush(c.q, rq, NX, NX, 0, 0, 2);
-                flush(c.r, rr, NU, NU, 0, 0, 0);
-                flush(c.c, rc0, NX, NX, 0, -(c.N - 1), 1);
+                flush(std::integral_constant<int, NX>{}, c.q, rq, NX, 0, 0, 2);
+                flush(std::integral_constant<int, NU>{}, c.r, rr, NU, 0, 0, 0);
+                flush(std::integral_constant<int, NX>{}, c.c, rc0, NX, 0, -(c.N - 1), 1);
                 return;
         }
         float fext[6];
@@ -275,8 +291,8 @@ __global__ void __launch_bounds__(32) k_kkt_fine(Ctx c)
                 constexpr int rB = 0, rc = NX * NU;
                 Items<P>::linearize_base(st, xux, c.dt, [&](int e, float v) { stage[(rB + e) * ST + lane] = v; }, [&](int e, float v) { stage[(rc + e) * ST + lane] = v; });
                 __syncwarp();
-                flush(c.Bm, rB, NX * NU, NX * NU, 0, 0, 2);
-                flush(c.c, rc, NX, NX, 0, 1, 2);
+                flush(std::integral_constant<int, NX * NU>{}, c.Bm, rB, NX * NU, 0, 0, 2);
+                flush(std::integral_constant<int, NX>{}, c.c, rc, NX, 0, 1, 2);
                 return;
         }
         const int col = kind - 2;  // column of A
@@ -285,7 +301,7 @@ __global__ void __launch_bounds__(32) k_kkt_fine(Ctx c)
                 if (col == cidx) Items<P>::template linearize_column<cidx / NQ, cidx % NQ>(st, xux + NQ, c.dt, [&](int e, float v) { stage[(e - cidx * NX) * ST + lane] = v; });
         });
         __syncwarp();
-        flush(c.A, 0, NX, NX * NX, col * NX, 0, 2);
+        flush(std::integral_constant<int, NX>{}, c.A, 0, NX * NX, col * NX, 0, 2);
 }
 
 #include "bsqp_linalg_kernels.cuh"  // k_schur, k_pcg
