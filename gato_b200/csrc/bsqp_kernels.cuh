@@ -142,24 +142,22 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
                         sfor<0, NX>([&](auto ic) { stage[(rc0 + ic) * ST + lane] = x0[ic] - c.xs[(size_t)b * NX + ic]; });
                 }
                 __syncwarp();
-                {  // Q and R: expand the staged entries, zeros elsewhere
+                {  // Q and R: expand the staged entries, zeros elsewhere ((item, element) pairs flattened over the lanes like flush)
                         const int nvalid = min(32, total - item0);
-                        for (int i = 0; i < nvalid; i++) {
-                                const int  rb = rowbase[i] & ~(1 << 30), ki = (rowbase[i] >> 30) & 1 ? c.N - 1 : 0;
-                                float*     dQ = c.Q + (size_t)rb * NX * NX;
-                                for (int e = lane; e < NX * NX; e += 32) {
-                                        const int r_ = e / NX, c_ = e % NX;
-                                        float     v = 0.0f;
-                                        if (r_ < NQ && c_ < NQ)
-                                                v = stage[(rQ + r_ * NQ + c_) * ST + i];
-                                        else if (r_ == c_)
-                                                v = stage[(rQd + r_ - NQ) * ST + i];
-                                        dQ[e] = v;
-                                }
-                                if (ki != c.N - 1) {
-                                        float* dR = c.R + (size_t)rb * NU * NU;
-                                        for (int e = lane; e < NU * NU; e += 32) dR[e] = (e / NU == e % NU) ? stage[(rR + e / NU) * ST + i] : 0.0f;
-                                }
+                        for (int f = lane; f < nvalid * NX * NX; f += 32) {
+                                const int i = f / (NX * NX), e = f - i * (NX * NX), r_ = e / NX, c_ = e - r_ * NX;
+                                float     v = 0.0f;
+                                if (r_ < NQ && c_ < NQ)
+                                        v = stage[(rQ + r_ * NQ + c_) * ST + i];
+                                else if (r_ == c_)
+                                        v = stage[(rQd + r_ - NQ) * ST + i];
+                                c.Q[(size_t)(rowbase[i] & ~(1 << 30)) * NX * NX + e] = v;
+                        }
+                        for (int f = lane; f < nvalid * NU * NU; f += 32) {
+                                const int i = f / (NU * NU), e = f - i * (NU * NU), r_ = e / NU, c_ = e - r_ * NU;
+                                const int rb = rowbase[i];
+                                if ((rb >> 30) & 1) continue;  // the terminal item has no R
+                                c.R[(size_t)rb * NU * NU + e] = (r_ == c_) ? stage[(rR + r_) * ST + i] : 0.0f;
                         }
                 }
                 flush(std::integral_constant<int, NX>{}, c.q, rq, NX, 0, 0, 2);
@@ -258,24 +256,22 @@ __global__ void __launch_bounds__(32) k_kkt_fine(Ctx c)
                         sfor<0, NX>([&](auto ic) { stage[(rc0 + ic) * ST + lane] = x0[ic] - c.xs[(size_t)b * NX + ic]; });
                 }
                 __syncwarp();
-                {
+                {  // Q and R: expand the staged entries, zeros elsewhere ((item, element) pairs flattened over the lanes like flush)
                         const int nvalid = min(32, total - item0);
-                        for (int i = 0; i < nvalid; i++) {
-                                const int  rb = rowbase[i] & ~(1 << 30), ki = (rowbase[i] >> 30) & 1 ? c.N - 1 : 0;
-                                float*     dQ = c.Q + (size_t)rb * NX * NX;
-                                for (int e = lane; e < NX * NX; e += 32) {
-                                        const int r_ = e / NX, c_ = e % NX;
-                                        float     v = 0.0f;
-                                        if (r_ < NQ && c_ < NQ)
-                                                v = stage[(rQ + r_ * NQ + c_) * ST + i];
-                                        else if (r_ == c_)
-                                                v = stage[(rQd + r_ - NQ) * ST + i];
-                                        dQ[e] = v;
-                                }
-                                if (ki != c.N - 1) {
-                                        float* dR = c.R + (size_t)rb * NU * NU;
-                                        for (int e = lane; e < NU * NU; e += 32) dR[e] = (e / NU == e % NU) ? stage[(rR + e / NU) * ST + i] : 0.0f;
-                                }
+                        for (int f = lane; f < nvalid * NX * NX; f += 32) {
+                                const int i = f / (NX * NX), e = f - i * (NX * NX), r_ = e / NX, c_ = e - r_ * NX;
+                                float     v = 0.0f;
+                                if (r_ < NQ && c_ < NQ)
+                                        v = stage[(rQ + r_ * NQ + c_) * ST + i];
+                                else if (r_ == c_)
+                                        v = stage[(rQd + r_ - NQ) * ST + i];
+                                c.Q[(size_t)(rowbase[i] & ~(1 << 30)) * NX * NX + e] = v;
+                        }
+                        for (int f = lane; f < nvalid * NU * NU; f += 32) {
+                                const int i = f / (NU * NU), e = f - i * (NU * NU), r_ = e / NU, c_ = e - r_ * NU;
+                                const int rb = rowbase[i];
+                                if ((rb >> 30) & 1) continue;  // the terminal item has no R
+                                c.R[(size_t)rb * NU * NU + e] = (r_ == c_) ? stage[(rR + r_) * ST + i] : 0.0f;
                         }
                 }
                 flush(std::integral_constant<int, NX>{}, c.q, rq, NX, 0, 0, 2);
