@@ -119,7 +119,9 @@ size_t pcg_smem_bytes(int N, int threads)
 {
         constexpr int NX = 2 * P::NQ;
         const size_t  n = (size_t)(N + 2) * NX;
-        return sizeof(float) * (2 * n + 64 + 64 * (threads / 32) + (size_t)N * NX * NX + (size_t)(N - 1) * NX * NX);
+        const size_t  k2 = (size_t)N * NX * NX + (size_t)(N - 1) * NX * NX;  // K2 scratch, then reused for ...
+        const size_t  pf = (size_t)dz_prefetch_floats<NX, P::NQ>(N);           // ... the prefetched dz operands
+        return sizeof(float) * (2 * n + 64 + 64 * (threads / 32) + std::max(k2, pf));
 }
 template<class P>
 int configure_kernels(gato_solver* s)
