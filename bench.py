@@ -40,9 +40,9 @@ _N, _NX, _NU = 32, 14, 7
 PCG_FLOATS_PER_SOLVE = (_N * 3 * _NX * _NX + _N * _NX * _NX + 3 * (_N + 2) * _NX + (_N - 1) * _NX * _NX + (_N - 1) * _NX * _NU + _N * _NX * _NX + (_N - 1) * _NU * _NU
                         + 2 * _N * _NX + 2 * (_N - 1) * _NU + (_N * (_NX + _NU) - _NU))
 PCG_BYTES_PER_SOLVE = 4 * PCG_FLOATS_PER_SOLVE
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_pcg launch at batch 512 (ncu --set full, cold caches; profiles/r01_v10_k_pcg_raw.csv).
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_pcg launch at batch 512 (ncu --set full, cold caches; profiles/r01_v14_k_pcg_raw.csv).
 # Above the algorithmic bytes because the 56-byte main blocks of P^-1 sit inside 168-byte rows: DRAM sectors are fetched whole.
-PCG_NCU_TRAFFIC_BYTES_B512 = 115.111168e6 + 5.829376e6
+PCG_NCU_TRAFFIC_BYTES_B512 = 115.122432e6 + 4.426496e6
 FP32_NOMINAL_TFLOPS = 74.4  # 148 SM x 128 lanes x 2 x 1.965 GHz (no fp32 number in MEASURED_PEAKS.json)
 
 
