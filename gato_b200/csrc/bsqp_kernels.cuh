@@ -43,6 +43,7 @@ struct Ctx {
         const float *xs, *ref, *fext;
         float *      Q, *R, *q, *r, *A, *Bm, *c, *Qinv, *Rinv;  // KKT blocks, reference layout [b][k][elements]
         float *      S, *Pinv, *gamma, *lambda, *dz;            // Schur system, dual, primal step
+        float*       Pmain;  // main (diagonal) blocks of P^-1 as k_schur produces them, packed [b][k][nx x nx row-major]; k_pcg builds the rest
         float *      rho, *drho, *merit, *merit_cur, *step;
         const float *mu, *pcg_tol;
         int*         conv;        // [B] "PCG performed 0 iterations" flags (bsqp.cuh:153)
@@ -300,7 +301,8 @@ __global__ void __launch_bounds__(32) k_kkt_fine(Ctx c)
         flush(std::integral_constant<int, NX>{}, c.A, 0, NX * NX, col * NX, 0, 2);
 }
 
-#include "bsqp_linalg_kernels.cuh"  // k_schur, k_pcg
+#include "bsqp_linalg_kernels.cuh"  // k_schur
+#include "bsqp_pcg_kernels.cuh"     // k_pcg, k_pcg_stream
 
 // =====================================================================================================
 // k_merit_ls: one CTA per solve, thread per (alpha, knot) — computeMeritBatchedKernel + lineSearchAndUpdateBatchedKernel

@@ -1,0 +1,672 @@
+// PCG kernels of the BSQP path (included by bsqp_kernels.cuh inside namespace gato):
+//
+//   k_pcg         CTA per solve, thread per matrix row: each thread keeps ITS ROW of S and of P^-1 (2 x 3nx floats) in registers for
+//                 the whole solve; only the two shared vectors (p, r) live in shared memory.  The rows arrive through the TMA unit
+//                 (cp.async.bulk + mbarrier), the row products run on Blackwell's packed FFMA2 / FADD2.  Builds the off-diagonal
+//                 preconditioner blocks, runs PCG with the reference's reduction trees, recovers dz and does the convergence
+//                 bookkeeping.  Replaces formSchurSystemBatchedKernel2 (schur_linsys.cuh:214-260), solvePCGBatchedKernel
+//                 (pcg.cuh:14-148, which re-reads S and P^-1 from global memory every iteration), computeDzBatchedKernel
+//                 (schur_linsys.cuh:316-431) and the host loop of bsqp.cuh:142-163.
+//   k_pcg_stream  the same for horizons whose system does not fit the register file: rows streamed from L2 every iteration.
+// -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_tree(float v)  // __shfl_down tree 16,8,4,2,1 -> lane 0 (linalg.cuh:215)
+{
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = v + __shfl_down_sync(0xffffffffu, v, off);
+        return v;
+}
+
+// The reference's row reduction (btdMatrixVectorProduct, linalg.cuh:197-216): lane l accumulates columns l and l+32,
+// then the shuffle tree 16,8,4,2,1.  Evaluated depth-first by one thread: val(l, s) = val(l, 2s) + val(l+s, 2s).
+template<int W, int L, int S>
+__device__ __forceinline__ float row_tree(const float (&m)[W], const float (&v)[W])
+{
+        if constexpr (S == 32) {
+                float p = fmaf(m[L], v[L], 0.0f);
+                if constexpr (L + 32 < W) p = fmaf(m[L + 32], v[L + 32], p);
+                return p;
+        } else {
+                const float lo = row_tree<W, L, 2 * S>(m, v);
+                const float hi = row_tree<W, L + S, 2 * S>(m, v);
+                return lo + hi;
+        }
+}
+
+// asynchronous global -> shared copies (cp.async, LDGSTS): BYTES per copy = the largest of 16/8/4 that divides the per-knot block size, so
+// that every solve's block is aligned to it
+template<int BYTES>
+__device__ __forceinline__ void cp_async_region(float* sdst, const float* gsrc, int nfloats, int tid, int nthreads)
+{
+        constexpr int  F = BYTES / 4;
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(sdst);
+        for (int i = tid; i < nfloats / F; i += nthreads) {
+                if constexpr (BYTES == 16)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * i), "l"(gsrc + 4 * i) : "memory");
+                else if constexpr (BYTES == 8)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + 8u * i), "l"(gsrc + 2 * i) : "memory");
+                else
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + 4u * i), "l"(gsrc + i) : "memory");
+        }
+}
+constexpr int cp_bytes(int block_floats) { return (block_floats * 4) % 16 == 0 ? 16 : ((block_floats * 4) % 8 == 0 ? 8 : 4); }
+constexpr int pad4(int x) { return (x + 3) / 4 * 4; }
+// dz_x,k = -Qinv_k (q_k - lambda_k + A_k^T lambda_{k+1}), dz_u,k = -Rinv_k (r_k + B_k^T lambda_{k+1}); the bracketed residuals are
+// stored back into q, r (computeDzBatchedKernel, schur_linsys.cuh:331-430).  One warp per knot; wbuf = 64 floats per warp.
+template<int NX, int NU, int LDV = NX>
+__device__ __forceinline__ void dz_phase(const Ctx& c, int b, int N, int n, int warp, int lane, int nwarps, float* dzbuf, const float* lam, const float* Ab, const float* Bb,
+                                         const float* Qib, const float* Rib, const float* qb, const float* rb)
+{
+        // lam: this solve's padded lambda; Ab, Bb, Qib, Rib, qb, rb: its A, B, Q^-1, R^-1, q, r blocks (knot k at k * block size) -- in global
+        // memory, or (k_pcg) prefetched to shared memory.  The residuals are written back to c.q / c.r in global memory either way.
+        constexpr int NX2 = NX * NX;
+        const size_t  kb = (size_t)b * N;
+        float*        wbuf = dzbuf + warp * 64;
+        const int     traj = (NX + NU) * N - NU;
+        for (int k = warp; k < N; k += nwarps) {
+                const float* lk = lam + (k + 1) * LDV;  // LDV: floats between consecutive blocks of lambda (NX: packed; kSlot: k_pcg's slotted vectors)
+                const float* lk1 = lam + (k + 2) * LDV;
+                __syncwarp();
+                if (lane < NX) {
+                        float scr = 0.0f;
+                        if (k < N - 1) {
+                                const float* Ak = Ab + (size_t)k * NX2;
+                                float        sum = 0.0f;
+#pragma unroll
+                                for (int j = 0; j < NX; j++) sum = fmaf(lk1[j], Ak[lane * NX + j], sum);
+                                scr = -sum;
+                        }
+                        scr = scr + lk[lane];
+                        wbuf[lane] = qb[(size_t)k * NX + lane] - scr;
+                } else if (lane >= 16 && lane < 16 + NU && k < N - 1) {
+                        const int    x = lane - 16;
+                        const float* Bk = Bb + (size_t)k * NX * NU;
+                        float        sum = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < NX; j++) sum = fmaf(lk1[j], Bk[x * NX + j], sum);
+                        wbuf[32 + x] = rb[(size_t)k * NU + x] - (-sum);
+                }
+                __syncwarp();
+                if (lane < NX) {
+                        const float* Qi = Qib + (size_t)k * NX2;
+                        float        sum = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < NX; j++) sum = fmaf(Qi[j * NX + lane], wbuf[j], sum);
+                        c.dz[(size_t)b * traj + (size_t)k * (NX + NU) + lane] = -1.0f * sum;
+                        c.q[(kb + k) * NX + lane] = wbuf[lane];
+                } else if (lane >= 16 && lane < 16 + NU) {
+                        const int x = lane - 16;
+                        if (k < N - 1) {
+                                const float* Ri = Rib + (size_t)k * NU * NU;
+                                float        sum = 0.0f;
+#pragma unroll
+                                for (int j = 0; j < NU; j++) sum = fmaf(Ri[j * NU + x], wbuf[32 + j], sum);
+                                c.dz[(size_t)b * traj + (size_t)k * (NX + NU) + NX + x] = -1.0f * sum;
+                                c.r[(kb + k) * NU + x] = wbuf[32 + x];
+                        } else {
+                                c.r[(kb + k) * NU + x] = 0.0f;
+                        }
+                }
+        }
+}
+
+// The warp's 32 consecutive rows r0 .. r0+31 of a block-tridiagonal matrix (row-major, W floats per row; rows outside [0, nrows) do not
+// exist) -> the warp's shared-memory tile, as coalesced 16-byte asynchronous copies (cp.async.cg: global -> shared without passing
+// through registers or L1).  Thread-per-row loads straight from global memory are 168-byte strided: every 32-byte sector is requested
+// four times and the kernel ends up bound by L1/L2 request throughput (ncu: L1/TEX 65 %, L2 56 %, DRAM 8 % -- the 148 solves in flight
+// fit in L2).  r0 and nrows are even, so both ends of the copy are 16-byte aligned.
+template<int W>
+__device__ __forceinline__ void warp_tile_load(float* tile, const float* gM, int r0, int nrows, int lane)
+{
+        __syncwarp();  // every lane is done reading the previous contents of the tile
+        const int lo = r0 > 0 ? r0 : 0, hi = (r0 + 32 < nrows) ? r0 + 32 : nrows;
+        if (hi > lo) {
+                const float*   src = gM + (size_t)lo * W;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + (lo - r0) * W);
+                const int      nchunk = (hi - lo) * W / 4;
+                for (int i = lane; i < nchunk; i += 32) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 4 * i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+}
+// ---- Blackwell / Hopper asynchronous-copy plumbing (PTX): mbarrier + bulk copies through the TMA unit (cp.async.bulk, SASS UBLKCP) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void     mbar_init(unsigned long long* bar, unsigned arrivals)
+{
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+// make the barrier initialisation visible to the asynchronous proxy (the TMA unit completes transactions on it)
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// order this thread's generic-proxy accesses to shared memory before later asynchronous-proxy (bulk copy) writes to the same bytes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// one contiguous span global -> shared, completion (bytes) signalled on the mbarrier; addresses and size are multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar)
+{
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+        unsigned done;
+        do {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        } while (!done);
+}
+
+constexpr int kSlot = 16;  // floats per block of the shared PCG vectors: every block starts 64-byte aligned, so a row's window is 3 x kSlot/4 LDS.128
+
+// (M v)[row] with the reference's reduction tree (btdMatrixVectorProduct, linalg.cuh:197-216: lane l accumulates columns l and l+32, then
+// the shuffle tree 16, 8, 4, 2, 1), evaluated by ONE thread on PACKED pairs: Blackwell's FFMA2 / FADD2 (fma.rn.f32x2, add.rn.f32x2) work
+// on two fp32 lanes per instruction, each rounded exactly like the scalar operation.  acc[j] = (leaf(2j), leaf(2j+1)); every level of the
+// tree adds pair j+h to pair j; the last level adds the two halves of the remaining pair.  win: the three kSlot-float blocks of the window.
+template<int NX>
+__device__ __forceinline__ float matvec_packed(const float2 (&M)[3 * NX / 2], const float* win)
+{
+        constexpr int W = 3 * NX, NP = W / 2, PPS = NX / 2;  // pairs per row, pairs per slot
+        static_assert(NX % 2 == 0 && W >= 32 && W <= 64 && NX <= kSlot, "row_tree geometry");
+        float2 v[NP];
+        sfor<0, 3>([&](auto sc) {
+                constexpr int sl = sc;
+                const float4* s4 = reinterpret_cast<const float4*>(win + sl * kSlot);
+                sfor<0, (NX + 3) / 4>([&](auto cc) {
+                        constexpr int ch = cc;
+                        const float4  t = s4[ch];
+                        v[sl * PPS + 2 * ch] = make_float2(t.x, t.y);
+                        if constexpr (2 * ch + 1 < PPS) v[sl * PPS + 2 * ch + 1] = make_float2(t.z, t.w);
+                });
+        });
+        float2 acc[16];
+        sfor<0, 16>([&](auto jc) { acc[jc] = __ffma2_rn(M[jc], v[jc], make_float2(0.0f, 0.0f)); });
+        sfor<16, NP>([&](auto jc) { acc[jc - 16] = __ffma2_rn(M[jc], v[jc], acc[jc - 16]); });
+        sfor<0, 8>([&](auto jc) { acc[jc] = __fadd2_rn(acc[jc], acc[jc + 8]); });
+        sfor<0, 4>([&](auto jc) { acc[jc] = __fadd2_rn(acc[jc], acc[jc + 4]); });
+        sfor<0, 2>([&](auto jc) { acc[jc] = __fadd2_rn(acc[jc], acc[jc + 2]); });
+        const float2 u = __fadd2_rn(acc[0], acc[1]);
+        return u.x + u.y;
+}
+
+// Second stage of block::dot (linalg.cuh:291-327): the reference's tree (shfl_down 16, 8, 4, 2, 1 over the per-warp partials; lanes beyond
+// the warp count hold +0.0f).  At most 16 warps: the offset-16 level only adds +0.0f, which is exact here -- a partial is never -0.0f (each
+// thread's term is fmaf(a, b, +0.0f), and sums of values that are not -0 are not -0).  Every thread evaluates lane 0's tree itself from
+// broadcast loads: one shared-memory latency and four dependent (packed) adds instead of four dependent shuffle levels and a broadcast.
+__device__ __forceinline__ float dot_final16(const float* scratch)
+{
+        const float4* s4 = reinterpret_cast<const float4*>(scratch);
+        const float4  a = s4[0], b = s4[1], c4 = s4[2], d = s4[3];  // entries >= #warps are +0.0f
+        const float2  t01 = __fadd2_rn(make_float2(a.x, a.y), make_float2(c4.x, c4.y)), t23 = __fadd2_rn(make_float2(a.z, a.w), make_float2(c4.z, c4.w));  // offset 8
+        const float2  u01 = __fadd2_rn(make_float2(b.x, b.y), make_float2(d.x, d.y)), u23 = __fadd2_rn(make_float2(b.z, b.w), make_float2(d.z, d.w));
+        const float2  w01 = __fadd2_rn(t01, u01), w23 = __fadd2_rn(t23, u23);  // offset 4
+        const float2  y = __fadd2_rn(w01, w23);                                // offset 2
+        return y.x + y.y;                                                      // offset 1
+}
+
+// Shared-memory layout of k_pcg (floats unless noted); the host sizes the launch with pcg_smem_floats().
+//   2 mbarriers (4 floats) | vp, vr: (N+2) blocks of kSlot floats each | scratchA(16) scratchB(16) | dz scratch (64 per warp) |
+//   stage A: the solve's S rows as the TMA unit delivers them (N*3*NX^2); once the rows are in registers: the K2 scratch ((N-1)*NX^2), then
+//            the prefetched operands of the primal step (A, B, Q^-1, R^-1, q, r)
+//   stage B: the packed main blocks of P^-1 (N*NX^2); after K2: the product blocks the right-hand P^-1 blocks are read from
+template<int NX, int NU>
+constexpr int dz_stage_floats(int N)
+{
+        return pad4(N * NX * NX) * 2 + pad4(N * NX * NU) + pad4(N * NU * NU) + pad4(N * NX) + pad4(N * NU);
+}
+template<int NX, int NU>
+constexpr size_t pcg_smem_floats(int N, int nwarps)
+{
+        const int stageA = 3 * N * NX * NX > dz_stage_floats<NX, NU>(N) ? 3 * N * NX * NX : dz_stage_floats<NX, NU>(N);
+        return 4 + 2 * (size_t)(N + 2) * kSlot + 32 + 64 * (size_t)nwarps + (size_t)stageA + (size_t)N * NX * NX;
+}
+// all six per-knot operand arrays of one solve can be moved by bulk copies (16-byte granularity) when N whole blocks of each are a
+// multiple of 16 bytes: then every solve's first block is 16-byte aligned as well
+template<int NX, int NU>
+__host__ __device__ constexpr bool dz_bulk_ok(int N)
+{
+        return (N * NX * NX) % 4 == 0 && (N * NX * NU) % 4 == 0 && (N * NU * NU) % 4 == 0 && (N * NX) % 4 == 0 && (N * NU) % 4 == 0;
+}
+
+// MAXT: the largest block the instantiation is launched with (480: iiwa14 up to N = 32; 512: everything else that fits a thread per padded index).
+template<class P, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_pcg(Ctx c)
+{
+        // Thread t owns PADDED vector index i = t (so real warp w == virtual warp w of the reference's block::dot) and, for
+        // NX <= i < NX + N*NX, matrix row r = i - NX: its rows of S and P^-1 and its elements of x, r, p live in registers, as float2 pairs.
+        constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ, NX2 = NX * NX, W = 3 * NX, NP = W / 2, HP = NX / 2;
+        if (stopped_before(c, c.it)) return;
+        extern __shared__ __align__(16) float sm[];
+        const int                             N = c.N, b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+        const int                             nrows = N * NX, n = (N + 2) * NX;
+        const int                             warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+        unsigned long long*                   bars = reinterpret_cast<unsigned long long*>(sm);  // [0]: rows staged, [1]: dz operands staged
+        float*                                vp = sm + 4;
+        float*                                vr = vp + (N + 2) * kSlot;
+        float*                                scratchA = vr + (N + 2) * kSlot;
+        float*                                scratchB = scratchA + 16;
+        float*                                dzbuf = scratchB + 16;
+        float*                                stageA = dzbuf + 64 * nwarps;
+        const int                             stageA_floats = 3 * N * NX2 > dz_stage_floats<NX, NU>(N) ? 3 * N * NX2 : dz_stage_floats<NX, NU>(N);
+        float*                                mains = stageA + stageA_floats;
+        const size_t                          kb = (size_t)b * N;
+        const float*                          gS = c.S + kb * 3 * NX2;
+        float*                                gP = c.Pinv + kb * 3 * NX2;
+        const int                             row = tid - NX;
+        const bool                            row_ok = (row >= 0) && (row < nrows);
+        const int                             br = row_ok ? row / NX : 0, ry = row_ok ? row % NX : 0;
+        const bool                            k2 = (c.flags & F_K2) != 0, need_rows = (c.flags & (F_K2 | F_PCG)) != 0;
+        const bool                            in_vec = tid < n;
+        const int                             own = (tid / NX) * kSlot + tid % NX;  // this thread's element of the slotted vectors
+
+        if (tid == 0) {
+                mbar_init(&bars[0], 1);
+                mbar_init(&bars[1], 1);
+                fence_mbar_init();
+        }
+        __syncthreads();
+        // The solve's rows of S (and the packed main blocks of P^-1) arrive as two bulk copies through the TMA unit: one thread issues them,
+        // the data lands in shared memory without passing through registers, and each thread then picks up its row with conflict-free
+        // 8-byte shared loads (a row is 3*NX floats: consecutive rows start 2*(3*NX/2 mod 16) banks apart).
+        if (tid == 0 && need_rows) {
+                const unsigned bS = sizeof(float) * 3 * N * NX2, bP = sizeof(float) * N * NX2;
+                mbar_arrive_expect_tx(&bars[0], bS + (k2 ? bP : 0u));
+                bulk_g2s(stageA, gS, bS, &bars[0]);
+                if (k2) bulk_g2s(mains, c.Pmain + kb * NX2, bP, &bars[0]);
+        }
+        for (int i = tid; i < 2 * (N + 2) * kSlot + 32; i += T) vp[i] = 0.0f;  // vp, vr (including the padding) and both dot scratch rows
+
+        float2 S2[NP], P2[NP];
+        sfor<0, NP>([&](auto ic) { S2[ic] = make_float2(0.0f, 0.0f), P2[ic] = make_float2(0.0f, 0.0f); });
+        if (need_rows) {
+                static_assert(NX % 2 == 0, "blocks are float2-aligned");
+                mbar_wait(&bars[0], 0);
+                if (row_ok) {
+                        const float2* s2 = reinterpret_cast<const float2*>(stageA + (size_t)row * W);
+                        sfor<0, NP>([&](auto ic) { S2[ic] = s2[ic]; });
+                        if (k2) {
+                                // only the main block exists so far; the others hold the zeros that row 0's left and row N-1's right block keep
+                                // (schur_linsys.cuh:227-259)
+                                const float2* p2 = reinterpret_cast<const float2*>(mains + (size_t)row * NX);
+                                sfor<0, HP>([&](auto ic) { P2[HP + ic] = p2[ic]; });
+                        } else {
+                                const float2* p2 = reinterpret_cast<const float2*>(gP + (size_t)row * W);  // stage test: complete rows, reference layout
+                                sfor<0, NP>([&](auto ic) { P2[ic] = __ldcs(p2 + ic); });
+                        }
+                }
+        }
+        if (k2) {
+                // left_{k+1} = -(Theta_k (phi_k Theta_{k-1})), right_k = left_{k+1}^T  (schur_linsys.cuh:227-259); Theta = the staged main blocks.
+                // Each 14-term chain runs over j in the reference's order; two neighbouring columns x, x+1 share one packed FFMA2.
+                __syncthreads();  // every row of S is in registers: stage A is free
+                float* scr2 = stageA;
+                if (row_ok && br >= 1) {
+                        // scr(y, x) = sum_j phi(y, j) * Theta_{k-1}(j, x), k = br-1; phi row y = this thread's S left block
+                        const float* tk1 = mains + (size_t)(br - 1) * NX2;
+                        float2       acc[HP];
+                        sfor<0, HP>([&](auto xc) { acc[xc] = make_float2(0.0f, 0.0f); });
+                        sfor<0, NX>([&](auto jc) {
+                                constexpr int j = jc;
+                                const float   a = (j & 1) ? S2[j / 2].y : S2[j / 2].x;
+                                const float2* t2 = reinterpret_cast<const float2*>(tk1 + j * NX);
+                                sfor<0, HP>([&](auto xc) { acc[xc] = __ffma2_rn(make_float2(a, a), t2[xc], acc[xc]); });
+                        });
+                        float2* o2 = reinterpret_cast<float2*>(scr2 + (size_t)(br - 1) * NX2 + ry * NX);
+                        sfor<0, HP>([&](auto xc) { o2[xc] = acc[xc]; });
+                }
+                __syncthreads();
+                float2 outrow[HP];
+                if (row_ok && br >= 1) {
+                        // out(y, x) = sum_j Theta_k(y, j) * scr(j, x); Theta_k row y = this thread's P main block
+                        const float* sc = scr2 + (size_t)(br - 1) * NX2;
+                        sfor<0, HP>([&](auto xc) { outrow[xc] = make_float2(0.0f, 0.0f); });
+                        sfor<0, NX>([&](auto jc) {
+                                constexpr int j = jc;
+                                const float   a = (j & 1) ? P2[HP + j / 2].y : P2[HP + j / 2].x;
+                                const float2* t2 = reinterpret_cast<const float2*>(sc + j * NX);
+                                sfor<0, HP>([&](auto xc) { outrow[xc] = __ffma2_rn(make_float2(a, a), t2[xc], outrow[xc]); });
+                        });
+                        sfor<0, HP>([&](auto xc) { P2[xc] = make_float2(-outrow[xc].x, -outrow[xc].y); });  // left block of this row
+                }
+                __syncthreads();  // everyone is done reading mains / scr2
+                if (row_ok && br >= 1) {
+                        float2* o2 = reinterpret_cast<float2*>(mains + (size_t)(br - 1) * NX2 + ry * NX);
+                        sfor<0, HP>([&](auto xc) { o2[xc] = outrow[xc]; });
+                }
+                __syncthreads();
+                if (row_ok && br < N - 1) {
+                        // right block of row (br, x = ry): entry (x, y) = -out_k(y, x), k = br
+                        const float* ok = mains + (size_t)br * NX2;
+                        sfor<0, HP>([&](auto yc) { P2[2 * HP + yc] = make_float2(-ok[(2 * yc) * NX + ry], -ok[(2 * yc + 1) * NX + ry]); });
+                }
+                if ((c.flags & F_WRITE_P) && row_ok) {
+                        float2* g2 = reinterpret_cast<float2*>(gP + (size_t)row * W);
+                        sfor<0, NP>([&](auto ic) { g2[ic] = P2[ic]; });
+                }
+        }
+
+        // The operands of the primal step (A, B, Q^-1, R^-1, q, r of this solve, 71 KB) were written two kernels ago and have left L2 by now:
+        // read on demand, each of the dz phase's dependent steps would wait for HBM.  They are prefetched into stage A (free once the rows
+        // are in registers and K2 is done) while the PCG iterations run -- six bulk copies through the TMA unit signalled on an mbarrier
+        // (or, for horizons whose per-solve arrays are not 16-byte multiples, cp.async) -- and lambda is left in shared memory by the PCG phase.
+        float* sA = stageA;
+        float* sB = sA + pad4(N * NX2);
+        float* sQi = sB + pad4(N * NX * NU);
+        float* sRi = sQi + pad4(N * NX2);
+        float* sq = sRi + pad4(N * NU * NU);
+        float* sr = sq + pad4(N * NX);
+        const bool bulk_dz = dz_bulk_ok<NX, NU>(N);
+        if (c.flags & F_DZ) {
+                fence_proxy_async();
+                __syncthreads();  // all generic accesses to stage A are done and ordered before the asynchronous writes
+                if (bulk_dz) {
+                        if (tid == 0) {
+                                const unsigned bA = 4u * N * NX2, bB = 4u * N * NX * NU, bR = 4u * N * NU * NU, bq = 4u * N * NX, br_ = 4u * N * NU;
+                                mbar_arrive_expect_tx(&bars[1], 2 * bA + bB + bR + bq + br_);
+                                bulk_g2s(sA, c.A + kb * NX2, bA, &bars[1]);
+                                bulk_g2s(sB, c.Bm + kb * NX * NU, bB, &bars[1]);
+                                bulk_g2s(sQi, c.Qinv + kb * NX2, bA, &bars[1]);
+                                bulk_g2s(sRi, c.Rinv + kb * NU * NU, bR, &bars[1]);
+                                bulk_g2s(sq, c.q + kb * NX, bq, &bars[1]);
+                                bulk_g2s(sr, c.r + kb * NU, br_, &bars[1]);
+                        }
+                } else {
+                        cp_async_region<cp_bytes(NX2)>(sA, c.A + kb * NX2, (N - 1) * NX2, tid, T);
+                        cp_async_region<cp_bytes(NX * NU)>(sB, c.Bm + kb * NX * NU, (N - 1) * NX * NU, tid, T);
+                        cp_async_region<cp_bytes(NX2)>(sQi, c.Qinv + kb * NX2, N * NX2, tid, T);
+                        cp_async_region<cp_bytes(NU * NU)>(sRi, c.Rinv + kb * NU * NU, (N - 1) * NU * NU, tid, T);
+                        cp_async_region<cp_bytes(NX)>(sq, c.q + kb * NX, N * NX, tid, T);
+                        cp_async_region<cp_bytes(NU)>(sr, c.r + kb * NU, (N - 1) * NU, tid, T);
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+        } else {
+                __syncthreads();
+        }
+
+        int iters = 0;
+        if (c.flags & F_PCG) {
+                const float* gam = c.gamma + (size_t)b * n;
+                float*       lam = c.lambda + (size_t)b * n;
+                const float  eps = c.pcg_tol[b];
+                const float  abs_tol = 1e-6f;
+                const bool   skip = c.conv[b] != 0;  // pcg.cuh:29-32
+                const float* wp = vp + br * kSlot;   // this row's window: blocks br-1, br, br+1 = padded blocks br .. br+2
+                const float* wr = vr + br * kSlot;
+                // block::dot (linalg.cuh:291-327): thread i contributes a_i*b_i, warp tree, then a tree over the warp sums.
+                // Phase 1 (before the barrier): per-warp partials; phase 2 (after it): every thread reduces the partials itself.
+                auto dot_partial = [&](float prod, float* scratch) {
+                        const float s = warp_tree(prod);
+                        if (lane == 0) scratch[warp] = s;
+                };
+                if (!skip) {
+                        float x_i = in_vec ? lam[tid] : 0.0f;
+                        if (in_vec) vp[own] = x_i;  // vp temporarily holds x for r = gamma - S x
+                        __syncthreads();
+                        float r_i = 0.0f, p_i = 0.0f, z_i = 0.0f;
+                        {
+                                const float sx = row_ok ? matvec_packed<NX>(S2, wp) : 0.0f;
+                                r_i = in_vec ? (gam[tid] - sx) : 0.0f;
+                                if (in_vec) vr[own] = r_i;
+                        }
+                        __syncthreads();
+                        z_i = row_ok ? matvec_packed<NX>(P2, wr) : 0.0f;
+                        p_i = z_i;
+                        if (in_vec) vp[own] = p_i;
+                        dot_partial(fmaf(r_i, z_i, 0.0f), scratchA);
+                        __syncthreads();
+                        float rho = dot_final16(scratchA);
+                        if (!(fabsf(rho) < abs_tol)) {
+                                const float rho_init = fabsf(rho);
+                                for (int itn = 0; itn < c.max_pcg; itn++) {
+                                        iters++;
+                                        const float Ap_i = row_ok ? matvec_packed<NX>(S2, wp) : 0.0f;
+                                        dot_partial(fmaf(p_i, Ap_i, 0.0f), scratchB);
+                                        __syncthreads();
+                                        const float alpha = rho / dot_final16(scratchB);
+                                        x_i = fmaf(alpha, p_i, x_i);
+                                        r_i = fmaf(-alpha, Ap_i, r_i);
+                                        if (in_vec) vr[own] = r_i;
+                                        __syncthreads();
+                                        z_i = row_ok ? matvec_packed<NX>(P2, wr) : 0.0f;
+                                        dot_partial(fmaf(r_i, z_i, 0.0f), scratchA);
+                                        __syncthreads();
+                                        const float rho_new = dot_final16(scratchA);
+                                        if (fabsf(rho_new) < fmaf(eps, rho_init, abs_tol)) break;
+                                        const float beta = rho_new / rho;
+                                        rho = rho_new;
+                                        p_i = fmaf(beta, p_i, z_i);
+                                        if (in_vec) vp[own] = p_i;
+                                        __syncthreads();
+                                }
+                                if (in_vec) lam[tid] = x_i;
+                        }
+                }
+                if (tid == 0) {
+                        if (c.pcg_log) c.pcg_log[(size_t)c.it * c.B + b] = iters;
+                        if (c.flags & F_BOOK) {
+                                // bsqp.cuh:153-163: a solve is flagged once PCG performs no iteration; count flagged solves
+                                int cv = c.conv[b];
+                                if (iters == 0) cv = 1;
+                                c.conv[b] = cv;
+                                if (cv) atomicAdd(&c.num_solved[c.it], 1u);
+                        }
+                }
+                __syncthreads();
+        }
+
+        if (c.flags & F_DZ) {
+                // lambda of this solve (possibly just updated by threads of this CTA) -> shared memory (vp is free now)
+                if (in_vec) vp[own] = c.lambda[(size_t)b * n + tid];
+                if (bulk_dz)
+                        mbar_wait(&bars[1], 0);
+                else
+                        asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncthreads();
+                dz_phase<NX, NU, kSlot>(c, b, N, n, warp, lane, nwarps, dzbuf, vp, sA, sB, sQi, sRi, sq, sr);
+        }
+}
+
+
+// -----------------------------------------------------------------------------------------------------
+// k_pcg_stream: the same algorithm for horizons whose Schur system does not fit the register file ((N+2)*nx > 512, e.g. N = 128):
+// 1024 threads (exactly the reference's PCG block, so thread t owns padded indices t, t+1024, ... like block::dot); the rows of S and
+// P^-1 are streamed in every matvec (what the reference does for every N, pcg.cuh:100,119) -- from L2, which holds the systems of the
+// 148 solves in flight -- through per-warp shared-memory tiles filled with coalesced asynchronous copies; the off-diagonal P^-1 blocks
+// are built through shared memory and written back to global memory first.
+// -----------------------------------------------------------------------------------------------------
+// this lane's row (already in the warp's tile) times the padded shared-memory vector v
+template<int NX>
+__device__ __forceinline__ float tile_row_matvec(const float* trow, int row, const float* v)
+{
+        constexpr int W = 3 * NX;
+        float         m[W], vv[W];
+        const float2* m2 = reinterpret_cast<const float2*>(trow);
+        const float2* v2 = reinterpret_cast<const float2*>(v + (row / NX) * NX);
+#pragma unroll
+        for (int i = 0; i < W / 2; i++) {
+                const float2 a = m2[i], t = v2[i];
+                m[2 * i] = a.x, m[2 * i + 1] = a.y;
+                vv[2 * i] = t.x, vv[2 * i + 1] = t.y;
+        }
+        return row_tree<W, 0, 1>(m, vv);
+}
+
+template<class P, int RPT>
+__global__ void __launch_bounds__(1024, 1) k_pcg_stream(Ctx c)
+{
+        constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ, NX2 = NX * NX, W = 3 * NX, T = 1024;
+        if (stopped_before(c, c.it)) return;
+        extern __shared__ __align__(16) float sm[];
+        // tid is read through asm so that the compiler has no range for it: with the [0,1024) range nvcc 12.9 folds
+        // sext((tid + c - NX) * W) into zext32(tid * W - NX * W) + c * W, wrong for tid < NX (seen in PTX; faulted at N = 128)
+        int tid;
+        asm("mov.u32 %0, %%tid.x;" : "=r"(tid));
+        const int N = c.N, b = blockIdx.x;
+        const int nrows = N * NX, n = (N + 2) * NX;
+        const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+        float*                                vp = sm;
+        float*                                vr = vp + n;
+        float*                                scratchA = vr + n;
+        float*                                scratchB = scratchA + 32;
+        float*                                dzbuf = scratchB + 32;
+        float*                                scr2 = dzbuf + 64 * nwarps;  // (N-1) * NX2 during K2; afterwards the 32 per-warp row tiles (32 x W floats each)
+        float*                                tile = scr2 + (size_t)warp * 32 * W;
+        const float*                          trow = tile + lane * W;
+        const size_t                          kb = (size_t)b * N;
+        const float*                          gS = c.S + kb * 3 * NX2;
+        float*                                gP = c.Pinv + kb * 3 * NX2;
+        for (int i = tid; i < 2 * n + 64; i += T) vp[i] = 0.0f;  // vp, vr and both dot scratch rows
+
+        if (c.flags & F_K2) {
+                // scr_k = phi_k Theta_{k-1};  out_k = Theta_k scr_k;  left_{k+1} = -out_k, right_k = -out_k^T   (schur_linsys.cuh:227-259)
+                const float* gPm = c.Pmain + kb * NX2;  // main blocks as k_schur packed them
+                for (int e = tid; e < (N - 1) * NX2; e += T) {
+                        const int    k = e / NX2, y = (e % NX2) / NX, x = e % NX;
+                        const float* ph = gS + (size_t)((k + 1) * NX + y) * W;  // S left block of row k+1, row y
+                        const float* tk1 = gPm + (size_t)k * NX2;               // main block of row k
+                        float        sum = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < NX; j++) sum = fmaf(ph[j], tk1[j * NX + x], sum);
+                        scr2[e] = sum;
+                }
+                // the streamed matvec reads complete rows in the reference layout: main blocks into place
+                for (int e = tid; e < N * NX2; e += T) gP[(size_t)(e / NX) * W + NX + e % NX] = gPm[e];
+                __syncthreads();
+                for (int e = tid; e < (N - 1) * NX2; e += T) {
+                        const int    k = e / NX2, y = (e % NX2) / NX, x = e % NX;
+                        const float* tk = gPm + (size_t)(k + 1) * NX2 + y * NX;  // main block of row k+1, row y
+                        const float* sc = scr2 + (size_t)k * NX2;
+                        float        sum = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < NX; j++) sum = fmaf(tk[j], sc[j * NX + x], sum);
+                        gP[(size_t)((k + 1) * NX + y) * W + x] = -sum;
+                        gP[(size_t)(k * NX + x) * W + 2 * NX + y] = -sum;
+                }
+                __threadfence_block();
+        }
+        __syncthreads();
+
+        int iters = 0;
+        if (c.flags & F_PCG) {
+                const float* gam = c.gamma + (size_t)b * n;
+                float*       lam = c.lambda + (size_t)b * n;
+                const float* gPc = gP;
+                const float  eps = c.pcg_tol[b];
+                const float  abs_tol = 1e-6f;
+                const bool   skip = c.conv[b] != 0;
+                if (!skip) {
+                        float x_[RPT], r_[RPT], p_[RPT], z_[RPT], Ap_[RPT];
+                        // thread t owns padded indices t, t+1024, ... (the reference's block::dot geometry, linalg.cuh:306)
+#pragma unroll
+                        for (int j = 0; j < RPT; j++) {
+                                const int i = tid + j * T;
+                                x_[j] = (i < n) ? lam[i] : 0.0f;
+                                if (i < n) vp[i] = x_[j];  // vp temporarily holds x for r = gamma - S x
+                        }
+                        __syncthreads();
+#pragma unroll
+                        for (int j = 0; j < RPT; j++) {
+                                const int   i = tid + j * T;
+                                const bool  rok = (i >= NX) && (i < NX + nrows);
+                                warp_tile_load<W>(tile, gS, warp * 32 + j * T - NX, nrows, lane);
+                                const float sx = rok ? tile_row_matvec<NX>(trow, i - NX, vp) : 0.0f;
+                                r_[j] = (i < n) ? (gam[i] - sx) : 0.0f;
+                                if (i < n) vr[i] = r_[j];
+                        }
+                        __syncthreads();
+                        float prod = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < RPT; j++) {
+                                const int  i = tid + j * T;
+                                const bool rok = (i >= NX) && (i < NX + nrows);
+                                warp_tile_load<W>(tile, gPc, warp * 32 + j * T - NX, nrows, lane);
+                                                z_[j] = rok ? tile_row_matvec<NX>(trow, i - NX, vr) : 0.0f;
+                                p_[j] = z_[j];
+                                prod = fmaf(r_[j], z_[j], prod);
+                        }
+                        __syncthreads();  // all reads of vp (as x) are done before it is overwritten with p
+#pragma unroll
+                        for (int j = 0; j < RPT; j++) {
+                                const int i = tid + j * T;
+                                if (i < n) vp[i] = p_[j];
+                        }
+                        {
+                                const float s = warp_tree(prod);
+                                if (lane == 0) scratchA[warp] = s;
+                        }
+                        __syncthreads();
+                        float rho = __shfl_sync(0xffffffffu, warp_tree(scratchA[lane]), 0);
+                        if (!(fabsf(rho) < abs_tol)) {
+                                const float rho_init = fabsf(rho);
+                                for (int itn = 0; itn < c.max_pcg; itn++) {
+                                        iters++;
+                                        prod = 0.0f;
+#pragma unroll
+                                        for (int j = 0; j < RPT; j++) {
+                                                const int  i = tid + j * T;
+                                                const bool rok = (i >= NX) && (i < NX + nrows);
+                                                warp_tile_load<W>(tile, gS, warp * 32 + j * T - NX, nrows, lane);
+                                                Ap_[j] = rok ? tile_row_matvec<NX>(trow, i - NX, vp) : 0.0f;
+                                                prod = fmaf(p_[j], Ap_[j], prod);
+                                        }
+                                        {
+                                                const float s = warp_tree(prod);
+                                                if (lane == 0) scratchB[warp] = s;
+                                        }
+                                        __syncthreads();
+                                        const float alpha = rho / __shfl_sync(0xffffffffu, warp_tree(scratchB[lane]), 0);
+#pragma unroll
+                                        for (int j = 0; j < RPT; j++) {
+                                                const int i = tid + j * T;
+                                                x_[j] = fmaf(alpha, p_[j], x_[j]);
+                                                r_[j] = fmaf(-alpha, Ap_[j], r_[j]);
+                                                if (i < n) vr[i] = r_[j];
+                                        }
+                                        __syncthreads();
+                                        prod = 0.0f;
+#pragma unroll
+                                        for (int j = 0; j < RPT; j++) {
+                                                const int  i = tid + j * T;
+                                                const bool rok = (i >= NX) && (i < NX + nrows);
+                                                warp_tile_load<W>(tile, gPc, warp * 32 + j * T - NX, nrows, lane);
+                                                z_[j] = rok ? tile_row_matvec<NX>(trow, i - NX, vr) : 0.0f;
+                                                prod = fmaf(r_[j], z_[j], prod);
+                                        }
+                                        {
+                                                const float s = warp_tree(prod);
+                                                if (lane == 0) scratchA[warp] = s;
+                                        }
+                                        __syncthreads();
+                                        const float rho_new = __shfl_sync(0xffffffffu, warp_tree(scratchA[lane]), 0);
+                                        if (fabsf(rho_new) < fmaf(eps, rho_init, abs_tol)) break;
+                                        const float beta = rho_new / rho;
+                                        rho = rho_new;
+#pragma unroll
+                                        for (int j = 0; j < RPT; j++) {
+                                                const int i = tid + j * T;
+                                                p_[j] = fmaf(beta, p_[j], z_[j]);
+                                                if (i < n) vp[i] = p_[j];
+                                        }
+                                        __syncthreads();
+                                }
+#pragma unroll
+                                for (int j = 0; j < RPT; j++) {
+                                        const int i = tid + j * T;
+                                        if (i < n) lam[i] = x_[j];
+                                }
+                        }
+                }
+                if (tid == 0) {
+                        if (c.pcg_log) c.pcg_log[(size_t)c.it * c.B + b] = iters;
+                        if (c.flags & F_BOOK) {
+                                int cv = c.conv[b];
+                                if (iters == 0) cv = 1;
+                                c.conv[b] = cv;
+                                if (cv) atomicAdd(&c.num_solved[c.it], 1u);
+                        }
+                }
+                __syncthreads();
+        }
+        if (c.flags & F_DZ)
+                dz_phase<NX, NU>(c, b, N, n, warp, lane, nwarps, dzbuf, c.lambda + (size_t)b * n, c.A + kb * NX2, c.Bm + kb * NX * NU, c.Qinv + kb * NX2, c.Rinv + kb * NU * NU, c.q + kb * NX,
+                                 c.r + kb * NU);
+}

@@ -85,15 +85,16 @@ struct gato_solver {
         std::vector<cudaEvent_t> tick_ev;
         std::vector<int>         tick_class;
         size_t                   n_ticks = 0;
-        int          max_it;
+        int          max_it;  // allocation size of the per-iteration logs: max(max_sqp_iters, 1)
+        int          n_it;    // SQP iterations enqueued per solve: max_sqp_iters (may be 0, bsqp.cuh:121)
         // device state
-        DevArr<float>    Q, R, q, r, A, Bm, c, Qinv, Rinv, S, Pinv, gamma, lambda, dz;
+        DevArr<float>    Q, R, q, r, A, Bm, c, Qinv, Rinv, S, Pinv, Pmain, gamma, lambda, dz;
         DevArr<float>    rho, drho, mu, pcg_tol, fext, merit, merit_cur, merit0, step, ls_merit_log, ls_step_log;
         DevArr<int>      conv, pcg_log;
         DevArr<unsigned> num_solved;
         DevArr<float>    st_xu, st_xs, st_ref, st_xkp1, st_xk, st_uk;  // staging for *_host calls
-        // host mirrors
-        std::vector<float> h_rho_init, h_drho_init;
+        // reset defaults of rho / drho (bsqp.cuh:48-58, 84-87, 189), resident on the device so that resets are device-to-device copies
+        DevArr<float> rho_init, drho_init;
         // pinned result buffers
         int *     h_pcg_log = nullptr, *h_conv = nullptr;
         unsigned* h_num_solved = nullptr;
@@ -104,7 +105,7 @@ struct gato_solver {
         size_t                                         smem_pcg = 0, smem_schur = 0;
         int                                            pcg_threads = 0, pcg_rpt = 0;
 
-        gato_solver(int plant_, int N_, int B_, int dev) : plant(plant_), N(N_), B(B_), device(dev), d(plant_ ? 7 : 6, N_), prm{}, max_it(1) {}
+        gato_solver(int plant_, int N_, int B_, int dev) : plant(plant_), N(N_), B(B_), device(dev), d(plant_ ? 7 : 6, N_), prm{}, max_it(1), n_it(1) {}
 };
 
 namespace {
@@ -117,11 +118,7 @@ int pcg_threads(int N)
 template<class P>
 size_t pcg_smem_bytes(int N, int threads)
 {
-        constexpr int NX = 2 * P::NQ;
-        const size_t  n = (size_t)(N + 2) * NX;
-        const size_t  k2 = (size_t)N * NX * NX + (size_t)(N - 1) * NX * NX;  // K2 scratch, then reused for ...
-        const size_t  pf = (size_t)dz_prefetch_floats<NX, P::NQ>(N);           // ... the prefetched dz operands
-        return sizeof(float) * (2 * n + 64 + 64 * (threads / 32) + std::max(k2, pf));
+        return sizeof(float) * pcg_smem_floats<2 * P::NQ, P::NQ>(N, threads / 32);
 }
 template<class P>
 int configure_kernels(gato_solver* s)
@@ -148,7 +145,7 @@ int configure_kernels(gato_solver* s)
                 s->err = "knot_points too large for the PCG kernel's shared memory on this device";
                 return GATO_ERR_UNSUPPORTED;
         }
-        CUDA_TRY(s, configure_linalg<P>(s->pcg_rpt, s->smem_pcg, s->smem_schur));
+        CUDA_TRY(s, configure_linalg<P>(s->device));
         return GATO_OK;
 }
 
@@ -161,7 +158,7 @@ Ctx make_ctx(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref,
         c.cs = Costs{s->prm.q_cost, s->prm.qd_cost, s->prm.u_cost, s->prm.N_cost, s->prm.q_lim_cost, s->prm.vel_lim_cost, s->prm.ctrl_lim_cost};
         c.xu = d_xu, c.xs = d_xs, c.ref = d_ref, c.fext = s->fext.p;
         c.Q = s->Q.p, c.R = s->R.p, c.q = s->q.p, c.r = s->r.p, c.A = s->A.p, c.Bm = s->Bm.p, c.c = s->c.p, c.Qinv = s->Qinv.p, c.Rinv = s->Rinv.p;
-        c.S = s->S.p, c.Pinv = s->Pinv.p, c.gamma = s->gamma.p, c.lambda = s->lambda.p, c.dz = s->dz.p;
+        c.S = s->S.p, c.Pinv = s->Pinv.p, c.Pmain = s->Pmain.p, c.gamma = s->gamma.p, c.lambda = s->lambda.p, c.dz = s->dz.p;
         c.rho = s->rho.p, c.drho = s->drho.p, c.merit = s->merit.p, c.merit_cur = s->merit_cur.p, c.step = s->step.p;
         c.mu = s->mu.p, c.pcg_tol = s->pcg_tol.p;
         c.conv = s->conv.p, c.num_solved = s->num_solved.p, c.pcg_log = s->pcg_log.p, c.ls_merit_log = s->ls_merit_log.p, c.ls_step_log = s->ls_step_log.p;
@@ -236,14 +233,18 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
                 tick(s, -1);
                 CUDA_TRY(s, cudaMemcpyAsync(s->merit0.p, s->merit_cur.p, sizeof(float) * B, cudaMemcpyDeviceToDevice, s->stream));
         }
-        for (int it = 0; it < s->max_it; it++) {
+        bool joined = !forked;
+        for (int it = 0; it < s->n_it; it++) {
                 c.it = it;
                 c.flags = F_CHECK_STOP;
                 launch_kkt<P>(s, c);
                 launch_schur<P>(s, c);
                 c.flags = F_CHECK_STOP | F_K2 | F_PCG | F_DZ | F_BOOK;
                 launch_pcg<P>(s, c);
-                if (it == 0 && forked) CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+                if (!joined) {
+                        CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+                        joined = true;
+                }
                 c.flags = F_CHECK_STOP | F_MERIT | F_LS;
                 launch_merit<P, kNumAlphas>(s, c);
         }
@@ -251,6 +252,7 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
         // merit of the last accepted line-search candidate, evaluated by k_merit_ls<8> at exactly the trajectory fmaf(step, dz, xu) that the
         // line search then stored (same expression, same knot-ordered sum), or -- if no step was ever accepted -- the initial merit of the
         // unchanged trajectory.  (The reference re-evaluates it with a fresh kernel.)
+        if (!joined) CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));  // max_sqp_iters = 0: only the merits are evaluated
         tick(s, -1);
         CUDA_TRY(s, cudaGetLastError());
         // results -> pinned host buffers
@@ -262,7 +264,7 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
         CUDA_TRY(s, cudaMemcpyAsync(s->h_final, s->merit_cur.p, sizeof(float) * B, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(s, cudaMemcpyAsync(s->h_initial, s->merit0.p, sizeof(float) * B, cudaMemcpyDeviceToHost, s->stream));
         // drho is reset after every solve (bsqp.cuh:189); lambda and rho persist
-        CUDA_TRY(s, cudaMemcpyAsync(s->drho.p, s->h_drho_init.data(), sizeof(float) * B, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->drho.p, s->drho_init.p, sizeof(float) * B, cudaMemcpyDeviceToDevice, s->stream));
         return GATO_OK;
 }
 
@@ -276,8 +278,8 @@ int fill_stats(gato_solver* s, gato_stats* st)
         const int B = s->B;
         // outer iterations executed: up to and including the first one whose count met the early-exit test (bsqp.cuh:165)
         const float thresh = (float)(uint32_t)B * s->prm.solve_ratio;
-        int         n_pcg = s->max_it, n_ls = s->max_it;
-        for (int i = 0; i < s->max_it; i++)
+        int         n_pcg = s->n_it, n_ls = s->n_it;
+        for (int i = 0; i < s->n_it; i++)
                 if ((float)s->h_num_solved[i] >= thresh) {
                         n_pcg = i + 1;
                         n_ls = i;
@@ -377,6 +379,7 @@ int gato_create(gato_solver** out, int plant, int N, int B, int device, void* st
         gato_solver* s = new gato_solver(plant, N, B, device);
         s->prm = *prm;
         s->max_it = (int)std::max<uint32_t>(prm->max_sqp_iters, 1u);
+        s->n_it = (int)prm->max_sqp_iters;
         auto fail = [&](int rc) {
                 g_create_error = s->err;
                 gato_destroy(s);
@@ -408,8 +411,8 @@ int gato_create(gato_solver** out, int plant, int N, int B, int device, void* st
         };
         A(s->Q, b * d.nx * d.nx * N), A(s->R, b * d.nu * d.nu * N), A(s->q, b * d.nx * N), A(s->r, b * d.nu * N), A(s->A, b * d.nx * d.nx * N), A(s->Bm, b * d.nx * d.nu * N);
         A(s->c, b * d.nx * N), A(s->Qinv, b * d.nx * d.nx * N), A(s->Rinv, b * d.nu * d.nu * N);
-        A(s->S, b * d.brow * N), A(s->Pinv, b * d.brow * N), A(s->gamma, b * d.vecp), A(s->lambda, b * d.vecp), A(s->dz, b * d.traj);
-        A(s->rho, b), A(s->drho, b), A(s->mu, b), A(s->pcg_tol, b), A(s->fext, 6 * b), A(s->merit, kNumAlphas * b), A(s->merit_cur, b), A(s->merit0, b), A(s->step, b);
+        A(s->S, b * d.brow * N), A(s->Pinv, b * d.brow * N), A(s->Pmain, b * d.nx * d.nx * N), A(s->gamma, b * d.vecp), A(s->lambda, b * d.vecp), A(s->dz, b * d.traj);
+        A(s->rho, b), A(s->drho, b), A(s->rho_init, b), A(s->drho_init, b), A(s->mu, b), A(s->pcg_tol, b), A(s->fext, 6 * b), A(s->merit, kNumAlphas * b), A(s->merit_cur, b), A(s->merit0, b), A(s->step, b);
         A(s->ls_merit_log, it * b), A(s->ls_step_log, it * b), A(s->conv, b), A(s->pcg_log, it * b), A(s->num_solved, it);
         A(s->st_xu, b * d.traj), A(s->st_xs, b * d.nx), A(s->st_ref, b * 6 * N), A(s->st_xkp1, b * d.nx), A(s->st_xk, d.nx), A(s->st_uk, d.nu);
         if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_pcg_log, sizeof(int) * it * b);
@@ -430,11 +433,11 @@ int gato_create(gato_solver** out, int plant, int N, int B, int device, void* st
         }
         s->h_sqp_iters.assign(B, 0);
         // per-batch hyper-parameters  (bsqp.cuh:48-58)
-        s->h_rho_init.assign(B, prm->rho);
-        s->h_drho_init.assign(B, 1.0f);
-        std::vector<float> mu(B, prm->mu), tol(B, prm->pcg_tol);
-        cudaMemcpy(s->rho.p, s->h_rho_init.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
-        cudaMemcpy(s->drho.p, s->h_drho_init.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
+        std::vector<float> rho0(B, prm->rho), drho0(B, 1.0f), mu(B, prm->mu), tol(B, prm->pcg_tol);
+        cudaMemcpy(s->rho.p, rho0.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
+        cudaMemcpy(s->drho.p, drho0.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
+        cudaMemcpy(s->rho_init.p, rho0.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
+        cudaMemcpy(s->drho_init.p, drho0.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
         cudaMemcpy(s->mu.p, mu.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
         cudaMemcpy(s->pcg_tol.p, tol.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
         if (cudaDeviceSynchronize() != cudaSuccess) {
@@ -450,7 +453,7 @@ void gato_destroy(gato_solver* s)
         if (!s) return;
         cudaSetDevice(s->device);
         if (s->stream) cudaStreamSynchronize(s->stream);
-        for (auto* a : {&s->Q, &s->R, &s->q, &s->r, &s->A, &s->Bm, &s->c, &s->Qinv, &s->Rinv, &s->S, &s->Pinv, &s->gamma, &s->lambda, &s->dz, &s->rho, &s->drho, &s->mu, &s->pcg_tol, &s->fext,
+        for (auto* a : {&s->Q, &s->R, &s->q, &s->r, &s->A, &s->Bm, &s->c, &s->Qinv, &s->Rinv, &s->S, &s->Pinv, &s->Pmain, &s->gamma, &s->lambda, &s->dz, &s->rho, &s->drho, &s->rho_init, &s->drho_init, &s->mu, &s->pcg_tol, &s->fext,
                         &s->merit, &s->merit_cur, &s->merit0, &s->step, &s->ls_merit_log, &s->ls_step_log, &s->st_xu, &s->st_xs, &s->st_ref, &s->st_xkp1, &s->st_xk, &s->st_uk})
                 a->release();
         s->conv.release(), s->pcg_log.release(), s->num_solved.release();
@@ -475,23 +478,18 @@ int gato_set_batch(gato_solver* s, int field, const float* h, int set_default)
         if (!s || !h) return GATO_ERR_ARG;
         if (check_dev(s)) return GATO_ERR_CUDA;
         const size_t B = s->B;
-        float*       dst = nullptr;
+        float *      dst = nullptr, *dflt = nullptr;
         size_t       n = B;
         switch (field) {
                 case GATO_F_EXT: dst = s->fext.p, n = 6 * B; break;
-                case GATO_RHO:
-                        dst = s->rho.p;
-                        if (set_default) s->h_rho_init.assign(h, h + B);
-                        break;
-                case GATO_DRHO:
-                        dst = s->drho.p;
-                        if (set_default) s->h_drho_init.assign(h, h + B);
-                        break;
+                case GATO_RHO: dst = s->rho.p, dflt = s->rho_init.p; break;
+                case GATO_DRHO: dst = s->drho.p, dflt = s->drho_init.p; break;
                 case GATO_MU: dst = s->mu.p; break;
                 case GATO_PCG_TOL: dst = s->pcg_tol.p; break;
                 default: s->err = "unknown batch field"; return GATO_ERR_ARG;
         }
         CUDA_TRY(s, cudaMemcpyAsync(dst, h, sizeof(float) * n, cudaMemcpyHostToDevice, s->stream));
+        if (set_default && dflt) CUDA_TRY(s, cudaMemcpyAsync(dflt, dst, sizeof(float) * n, cudaMemcpyDeviceToDevice, s->stream));
         CUDA_TRY(s, cudaStreamSynchronize(s->stream));
         return GATO_OK;
 }
@@ -503,8 +501,8 @@ int gato_reset(gato_solver* s, int field)
         if (field == GATO_RESET_DUAL) {
                 CUDA_TRY(s, cudaMemsetAsync(s->lambda.p, 0, sizeof(float) * s->lambda.n, s->stream));
         } else if (field == GATO_RESET_RHO) {
-                CUDA_TRY(s, cudaMemcpyAsync(s->rho.p, s->h_rho_init.data(), sizeof(float) * s->B, cudaMemcpyHostToDevice, s->stream));
-                CUDA_TRY(s, cudaMemcpyAsync(s->drho.p, s->h_drho_init.data(), sizeof(float) * s->B, cudaMemcpyHostToDevice, s->stream));
+                CUDA_TRY(s, cudaMemcpyAsync(s->rho.p, s->rho_init.p, sizeof(float) * s->B, cudaMemcpyDeviceToDevice, s->stream));
+                CUDA_TRY(s, cudaMemcpyAsync(s->drho.p, s->drho_init.p, sizeof(float) * s->B, cudaMemcpyDeviceToDevice, s->stream));
         } else {
                 s->err = "unknown reset field";
                 return GATO_ERR_ARG;
@@ -586,8 +584,14 @@ int gato_get_merits(gato_solver* s, float* h_final, float* h_initial)
 {
         if (!s) return GATO_ERR_ARG;
         if (check_dev(s)) return GATO_ERR_CUDA;
-        if (h_final) CUDA_TRY(s, cudaMemcpy(h_final, s->merit_cur.p, sizeof(float) * s->B, cudaMemcpyDeviceToHost));
-        if (h_initial) CUDA_TRY(s, cudaMemcpy(h_initial, s->merit0.p, sizeof(float) * s->B, cudaMemcpyDeviceToHost));
+        if (s->pending) {
+                s->err = "gato_get_merits: a solve is still pending (call gato_solve_wait first)";
+                return GATO_ERR_ARG;
+        }
+        // ordered after everything enqueued on the solver's (non-blocking) stream
+        if (h_final) CUDA_TRY(s, cudaMemcpyAsync(h_final, s->merit_cur.p, sizeof(float) * s->B, cudaMemcpyDeviceToHost, s->stream));
+        if (h_initial) CUDA_TRY(s, cudaMemcpyAsync(h_initial, s->merit0.p, sizeof(float) * s->B, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
         return GATO_OK;
 }
 
@@ -787,8 +791,8 @@ int gato_mpc_step(gato_solver* s, const float* h_x_curr, const float* h_ref_wind
         k_mpc_prepare<<<B, 64, 0, s->stream>>>(B, d.nx, d.N, d.traj, s->mpc_in.p, s->mpc_has_off ? s->mpc_off.p : nullptr, s->mpc_xs.p, s->mpc_ref.p, s->mpc_xu.p);
         s->launches++;
         if (flags & GATO_MPC_RESET_RHO) {
-                CUDA_TRY(s, cudaMemcpyAsync(s->rho.p, s->h_rho_init.data(), sizeof(float) * B, cudaMemcpyHostToDevice, s->stream));
-                CUDA_TRY(s, cudaMemcpyAsync(s->drho.p, s->h_drho_init.data(), sizeof(float) * B, cudaMemcpyHostToDevice, s->stream));
+                CUDA_TRY(s, cudaMemcpyAsync(s->rho.p, s->rho_init.p, sizeof(float) * B, cudaMemcpyDeviceToDevice, s->stream));
+                CUDA_TRY(s, cudaMemcpyAsync(s->drho.p, s->drho_init.p, sizeof(float) * B, cudaMemcpyDeviceToDevice, s->stream));
         }
         if (int rc = dispatch_enqueue(s, s->mpc_xu.p, s->mpc_xs.p, s->mpc_ref.p, timestep)) return rc;
         float* d_best_out = s->mpc_xnext.p + (size_t)B * d.nx;

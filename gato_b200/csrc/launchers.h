@@ -20,9 +20,9 @@ void enqueue_schur(const Ctx& c, size_t smem, cudaStream_t st);
 // rpt = 0: register-resident k_pcg with `threads` threads; rpt = 1..4: k_pcg_stream<rpt> with 1024 threads
 template<class P>
 void enqueue_pcg(const Ctx& c, int rpt, int threads, size_t smem, cudaStream_t st);
-// opt in to the dynamic shared memory the linear-algebra kernels need
+// opt in to the device's maximum dynamic shared memory for every linear-algebra kernel (the attribute is global per kernel and device)
 template<class P>
-cudaError_t configure_linalg(int rpt, size_t smem_pcg, size_t smem_schur);
+cudaError_t configure_linalg(int device);
 template<class P>
 size_t schur_smem_bytes();
 // num_alphas = 1 (initial / final merit) or kNumAlphas (merit + line search)

@@ -29,21 +29,32 @@ void enqueue_pcg<GATO_TU_PLANT>(const Ctx& c, int rpt, int threads, size_t smem,
                 default: k_pcg_stream<P, 4><<<c.B, 1024, smem, st>>>(c); break;
         }
 }
+namespace {
+// cudaFuncAttributeMaxDynamicSharedMemorySize is global per kernel and device: it is always raised to the device's opt-in maximum (minus
+// the kernel's static shared memory), never to what one solver happens to need, so that solvers with different horizons can coexist.
+template<class K>
+cudaError_t opt_in_max_smem(K kernel, int device)
+{
+        int         maxopt = 0;
+        cudaError_t e = cudaDeviceGetAttribute(&maxopt, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        if (e != cudaSuccess) return e;
+        cudaFuncAttributes fa{};
+        e = cudaFuncGetAttributes(&fa, kernel);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxopt - (int)fa.sharedSizeBytes);
+}
+}  // namespace
 template<>
-cudaError_t configure_linalg<GATO_TU_PLANT>(int rpt, size_t smem_pcg, size_t smem_schur)
+cudaError_t configure_linalg<GATO_TU_PLANT>(int device)
 {
         using P = GATO_TU_PLANT;
-        cudaError_t e = cudaFuncSetAttribute(k_schur<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_schur);
-        if (e != cudaSuccess) return e;
-        switch (rpt) {
-                case 0:
-                        e = cudaFuncSetAttribute(k_pcg<P, 480>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pcg);
-                        if (e != cudaSuccess) return e;
-                        return cudaFuncSetAttribute(k_pcg<P, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pcg);
-                case 1: return cudaFuncSetAttribute(k_pcg_stream<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pcg);
-                case 2: return cudaFuncSetAttribute(k_pcg_stream<P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pcg);
-                case 3: return cudaFuncSetAttribute(k_pcg_stream<P, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pcg);
-                default: return cudaFuncSetAttribute(k_pcg_stream<P, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pcg);
-        }
+        cudaError_t e = opt_in_max_smem(k_schur<P>, device);
+        if (e == cudaSuccess) e = opt_in_max_smem(k_pcg<P, 480>, device);
+        if (e == cudaSuccess) e = opt_in_max_smem(k_pcg<P, 512>, device);
+        if (e == cudaSuccess) e = opt_in_max_smem(k_pcg_stream<P, 1>, device);
+        if (e == cudaSuccess) e = opt_in_max_smem(k_pcg_stream<P, 2>, device);
+        if (e == cudaSuccess) e = opt_in_max_smem(k_pcg_stream<P, 3>, device);
+        if (e == cudaSuccess) e = opt_in_max_smem(k_pcg_stream<P, 4>, device);
+        return e;
 }
 }  // namespace gato

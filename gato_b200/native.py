@@ -85,6 +85,8 @@ def load():
     lib.gato_get_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.gato_get_launch_times.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]
     lib.gato_get_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    if hasattr(lib, "gato_measure_fp32_peak"):  # absent from older builds loaded through GATO_B200_LIB for A/B runs
+        lib.gato_measure_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     lead = [C.c_int, C.c_int, C.c_int]
     lib.gato_stage_kkt.argtypes = lead + [f32p] * 4 + [C.c_float, f32p] + [f32p] * 7
     lib.gato_stage_schur.argtypes = lead + [f32p] * 11
@@ -94,6 +96,15 @@ def load():
     lib.gato_stage_linesearch.argtypes = lead + [f32p] * 7 + [C.c_int]
     _LIB = lib
     return lib
+
+
+def measure_fp32_peak(device=0, packed=True):
+    """Measured FP32 FMA peak of the device in TFLOP/s (scalar FFMA or packed FFMA2)."""
+    out = C.c_double()
+    rc = load().gato_measure_fp32_peak(int(device), int(bool(packed)), C.byref(out))
+    if rc != 0:
+        raise GatoError(f"gato_measure_fp32_peak failed ({rc})")
+    return float(out.value)
 
 
 def make_params(p):

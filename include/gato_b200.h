@@ -121,6 +121,11 @@ int gato_get_kernel_times(gato_solver* s, float* total_ms /* [5] */, int* launch
 /* every launch of the last completed solve in launch order: class id and duration; returns the number of launches written (<= cap) or < 0 */
 int gato_get_launch_times(gato_solver* s, int* kernel_class, float* ms, int cap);
 
+/* Measured FP32 CUDA-core peak of `device` in TFLOP/s (the denominator of the FP32 roofline fractions bench.py
+ * reports; MEASURED_PEAKS.json has no FP32 number): a register-resident fused-multiply-add loop at full occupancy, packed = 0 scalar FFMA,
+ * packed = 1 Blackwell's two-wide FFMA2 (what the linear-algebra kernels of this library issue).  Measurement aid, not on the solve path. */
+int gato_measure_fp32_peak(int device, int packed, double* tflops);
+
 /* Stage-level entry points (host buffers; used by the parity tests, same layouts as the reference kernels'
  * global buffers — setup_kkt.cuh:15, schur_linsys.cuh:14/214/316, pcg.cuh:14, merit.cuh:17, line_search.cuh:13). */
 int gato_stage_kkt(int plant, int N, int B, const float* xu, const float* xs, const float* ref, const float* fext, float dt, const float* cost7, float* Q, float* R, float* q, float* r, float* A,
