@@ -9,6 +9,12 @@
 //                 (schur_linsys.cuh:316-431) and the host loop of bsqp.cuh:142-163.
 //   k_pcg_stream  the same for horizons whose system does not fit the register file: rows streamed from L2 every iteration.
 // -----------------------------------------------------------------------------------------------------
+#pragma once
+#include "bsqp_ctx.cuh"
+#include "pcg_layout.h"
+#include "sfor.h"
+
+namespace gato {
 __device__ __forceinline__ float warp_tree(float v)  // __shfl_down tree 16,8,4,2,1 -> lane 0 (linalg.cuh:215)
 {
 #pragma unroll
@@ -49,7 +55,6 @@ __device__ __forceinline__ void cp_async_region(float* sdst, const float* gsrc, 
         }
 }
 constexpr int cp_bytes(int block_floats) { return (block_floats * 4) % 16 == 0 ? 16 : ((block_floats * 4) % 8 == 0 ? 8 : 4); }
-constexpr int pad4(int x) { return (x + 3) / 4 * 4; }
 // dz_x,k = -Qinv_k (q_k - lambda_k + A_k^T lambda_{k+1}), dz_u,k = -Rinv_k (r_k + B_k^T lambda_{k+1}); the bracketed residuals are
 // stored back into q, r (computeDzBatchedKernel, schur_linsys.cuh:331-430).  One warp per knot; wbuf = 64 floats per warp.
 template<int NX, int NU, int LDV = NX>
@@ -156,26 +161,43 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         } while (!done);
 }
 
-constexpr int kSlot = 16;  // floats per block of the shared PCG vectors: every block starts 64-byte aligned, so a row's window is 3 x kSlot/4 LDS.128
+// shared-memory accesses of the PCG iteration on 32-bit shared-window addresses held in registers (the generic-pointer forms make the
+// compiler re-derive the window base from SR_CgaCtaId inside the loop, on the critical path between the reduction stages)
+__device__ __forceinline__ float4 lds128(unsigned a)
+{
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+        return v;
+}
+__device__ __forceinline__ float2 lds64(unsigned a)
+{
+        float2 v;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+        return v;
+}
+__device__ __forceinline__ void sts32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
 // (M v)[row] with the reference's reduction tree (btdMatrixVectorProduct, linalg.cuh:197-216: lane l accumulates columns l and l+32, then
 // the shuffle tree 16, 8, 4, 2, 1), evaluated by ONE thread on PACKED pairs: Blackwell's FFMA2 / FADD2 (fma.rn.f32x2, add.rn.f32x2) work
 // on two fp32 lanes per instruction, each rounded exactly like the scalar operation.  acc[j] = (leaf(2j), leaf(2j+1)); every level of the
-// tree adds pair j+h to pair j; the last level adds the two halves of the remaining pair.  win: the three kSlot-float blocks of the window.
+// tree adds pair j+h to pair j; the last level adds the two halves of the remaining pair.  win: shared address of the window's first block.
 template<int NX>
-__device__ __forceinline__ float matvec_packed(const float2 (&M)[3 * NX / 2], const float* win)
+__device__ __forceinline__ float matvec_packed(const float2 (&M)[3 * NX / 2], unsigned win)
 {
         constexpr int W = 3 * NX, NP = W / 2, PPS = NX / 2;  // pairs per row, pairs per slot
         static_assert(NX % 2 == 0 && W >= 32 && W <= 64 && NX <= kSlot, "row_tree geometry");
         float2 v[NP];
         sfor<0, 3>([&](auto sc) {
                 constexpr int sl = sc;
-                const float4* s4 = reinterpret_cast<const float4*>(win + sl * kSlot);
                 sfor<0, (NX + 3) / 4>([&](auto cc) {
                         constexpr int ch = cc;
-                        const float4  t = s4[ch];
-                        v[sl * PPS + 2 * ch] = make_float2(t.x, t.y);
-                        if constexpr (2 * ch + 1 < PPS) v[sl * PPS + 2 * ch + 1] = make_float2(t.z, t.w);
+                        if constexpr (2 * ch + 1 < PPS) {
+                                const float4 t = lds128(win + 4u * (sl * kSlot + 4 * ch));
+                                v[sl * PPS + 2 * ch] = make_float2(t.x, t.y);
+                                v[sl * PPS + 2 * ch + 1] = make_float2(t.z, t.w);
+                        } else {
+                                v[sl * PPS + 2 * ch] = lds64(win + 4u * (sl * kSlot + 4 * ch));
+                        }
                 });
         });
         float2 acc[16];
@@ -188,43 +210,44 @@ __device__ __forceinline__ float matvec_packed(const float2 (&M)[3 * NX / 2], co
         return u.x + u.y;
 }
 
-// Second stage of block::dot (linalg.cuh:291-327): the reference's tree (shfl_down 16, 8, 4, 2, 1 over the per-warp partials; lanes beyond
-// the warp count hold +0.0f).  At most 16 warps: the offset-16 level only adds +0.0f, which is exact here -- a partial is never -0.0f (each
-// thread's term is fmaf(a, b, +0.0f), and sums of values that are not -0 are not -0).  Every thread evaluates lane 0's tree itself from
-// broadcast loads: one shared-memory latency and four dependent (packed) adds instead of four dependent shuffle levels and a broadcast.
-__device__ __forceinline__ float dot_final16(const float* scratch)
+#ifndef GATO_PCG_DOT_STAGE1
+#define GATO_PCG_DOT_STAGE1 0
+#endif
+#ifndef GATO_PCG_DOT_STAGE2
+#define GATO_PCG_DOT_STAGE2 0
+#endif
+// block::dot (linalg.cuh:291-327): thread i contributes a_i * b_i; warp tree (shfl_down 16, 8, 4, 2, 1); lane 0 -> scratch[warp]; then the
+// same tree over the per-warp sums (lanes beyond the warp count hold +0.0f).  Both trees are evaluated by ONE lane from shared memory on
+// packed adds instead of as five dependent shuffle round trips: every lane drops its product into the warp's 32-float row, lane 0 folds the
+// row (offset 16: elements l and l+16 ... offset 1: the two halves of the last pair) and publishes the warp's sum.
+//   tree32: the 32 floats at shared address a -> lane 0's value of the reference's shuffle tree
+__device__ __forceinline__ float tree32(unsigned a)
 {
-        const float4* s4 = reinterpret_cast<const float4*>(scratch);
-        const float4  a = s4[0], b = s4[1], c4 = s4[2], d = s4[3];  // entries >= #warps are +0.0f
-        const float2  t01 = __fadd2_rn(make_float2(a.x, a.y), make_float2(c4.x, c4.y)), t23 = __fadd2_rn(make_float2(a.z, a.w), make_float2(c4.z, c4.w));  // offset 8
-        const float2  u01 = __fadd2_rn(make_float2(b.x, b.y), make_float2(d.x, d.y)), u23 = __fadd2_rn(make_float2(b.z, b.w), make_float2(d.z, d.w));
-        const float2  w01 = __fadd2_rn(t01, u01), w23 = __fadd2_rn(t23, u23);  // offset 4
-        const float2  y = __fadd2_rn(w01, w23);                                // offset 2
-        return y.x + y.y;                                                      // offset 1
+        float4 e[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) e[i] = lds128(a + 16u * i);
+        float2 t[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {  // offset 16: elements 4i..4i+3 with 16+4i..16+4i+3
+                t[2 * i] = __fadd2_rn(make_float2(e[i].x, e[i].y), make_float2(e[i + 4].x, e[i + 4].y));
+                t[2 * i + 1] = __fadd2_rn(make_float2(e[i].z, e[i].w), make_float2(e[i + 4].z, e[i + 4].w));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) t[i] = __fadd2_rn(t[i], t[i + 4]);  // offset 8
+        t[0] = __fadd2_rn(t[0], t[2]), t[1] = __fadd2_rn(t[1], t[3]);   // offset 4
+        const float2 y = __fadd2_rn(t[0], t[1]);                        // offset 2
+        return y.x + y.y;                                               // offset 1
 }
-
-// Shared-memory layout of k_pcg (floats unless noted); the host sizes the launch with pcg_smem_floats().
-//   2 mbarriers (4 floats) | vp, vr: (N+2) blocks of kSlot floats each | scratchA(16) scratchB(16) | dz scratch (64 per warp) |
-//   stage A: the solve's S rows as the TMA unit delivers them (N*3*NX^2); once the rows are in registers: the K2 scratch ((N-1)*NX^2), then
-//            the prefetched operands of the primal step (A, B, Q^-1, R^-1, q, r)
-//   stage B: the packed main blocks of P^-1 (N*NX^2); after K2: the product blocks the right-hand P^-1 blocks are read from
-template<int NX, int NU>
-constexpr int dz_stage_floats(int N)
+//   tree16: the second stage over at most 16 per-warp sums: the offset-16 level only adds +0.0f, which is exact here -- a partial is never
+//   -0.0f (each thread's term is fmaf(a, b, +0.0f), and sums of values that are not -0 are not -0)
+__device__ __forceinline__ float tree16(unsigned a)
 {
-        return pad4(N * NX * NX) * 2 + pad4(N * NX * NU) + pad4(N * NU * NU) + pad4(N * NX) + pad4(N * NU);
-}
-template<int NX, int NU>
-constexpr size_t pcg_smem_floats(int N, int nwarps)
-{
-        const int stageA = 3 * N * NX * NX > dz_stage_floats<NX, NU>(N) ? 3 * N * NX * NX : dz_stage_floats<NX, NU>(N);
-        return 4 + 2 * (size_t)(N + 2) * kSlot + 32 + 64 * (size_t)nwarps + (size_t)stageA + (size_t)N * NX * NX;
-}
-// all six per-knot operand arrays of one solve can be moved by bulk copies (16-byte granularity) when N whole blocks of each are a
-// multiple of 16 bytes: then every solve's first block is 16-byte aligned as well
-template<int NX, int NU>
-__host__ __device__ constexpr bool dz_bulk_ok(int N)
-{
-        return (N * NX * NX) % 4 == 0 && (N * NX * NU) % 4 == 0 && (N * NU * NU) % 4 == 0 && (N * NX) % 4 == 0 && (N * NU) % 4 == 0;
+        const float4 p = lds128(a), q = lds128(a + 16u), r = lds128(a + 32u), w = lds128(a + 48u);  // entries >= #warps are +0.0f
+        const float2 t01 = __fadd2_rn(make_float2(p.x, p.y), make_float2(r.x, r.y)), t23 = __fadd2_rn(make_float2(p.z, p.w), make_float2(r.z, r.w));  // offset 8
+        const float2 u01 = __fadd2_rn(make_float2(q.x, q.y), make_float2(w.x, w.y)), u23 = __fadd2_rn(make_float2(q.z, q.w), make_float2(w.z, w.w));
+        const float2 w01 = __fadd2_rn(t01, u01), w23 = __fadd2_rn(t23, u23);  // offset 4
+        const float2 y = __fadd2_rn(w01, w23);                                // offset 2
+        return y.x + y.y;                                                     // offset 1
 }
 
 // MAXT: the largest block the instantiation is launched with (480: iiwa14 up to N = 32; 512: everything else that fits a thread per padded index).
@@ -244,7 +267,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_pcg(Ctx c)
         float*                                vr = vp + (N + 2) * kSlot;
         float*                                scratchA = vr + (N + 2) * kSlot;
         float*                                scratchB = scratchA + 16;
-        float*                                dzbuf = scratchB + 16;
+        float*                                prod = scratchB + 16;  // one 32-float row per warp: the lanes' dot-product terms
+        float*                                dzbuf = prod + 32 * nwarps;
         float*                                stageA = dzbuf + 64 * nwarps;
         const int                             stageA_floats = 3 * N * NX2 > dz_stage_floats<NX, NU>(N) ? 3 * N * NX2 : dz_stage_floats<NX, NU>(N);
         float*                                mains = stageA + stageA_floats;
@@ -273,7 +297,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pcg(Ctx c)
                 bulk_g2s(stageA, gS, bS, &bars[0]);
                 if (k2) bulk_g2s(mains, c.Pmain + kb * NX2, bP, &bars[0]);
         }
-        for (int i = tid; i < 2 * (N + 2) * kSlot + 32; i += T) vp[i] = 0.0f;  // vp, vr (including the padding) and both dot scratch rows
+        for (int i = tid; i < 2 * (N + 2) * kSlot + 32 + 32 * nwarps; i += T) vp[i] = 0.0f;  // vp, vr (including the padding), both dot scratch rows, products
 
         float2 S2[NP], P2[NP];
         sfor<0, NP>([&](auto ic) { S2[ic] = make_float2(0.0f, 0.0f), P2[ic] = make_float2(0.0f, 0.0f); });
@@ -389,52 +413,70 @@ __global__ void __launch_bounds__(MAXT, 1) k_pcg(Ctx c)
                 const float  eps = c.pcg_tol[b];
                 const float  abs_tol = 1e-6f;
                 const bool   skip = c.conv[b] != 0;  // pcg.cuh:29-32
-                const float* wp = vp + br * kSlot;   // this row's window: blocks br-1, br, br+1 = padded blocks br .. br+2
-                const float* wr = vr + br * kSlot;
-                // block::dot (linalg.cuh:291-327): thread i contributes a_i*b_i, warp tree, then a tree over the warp sums.
-                // Phase 1 (before the barrier): per-warp partials; phase 2 (after it): every thread reduces the partials itself.
-                auto dot_partial = [&](float prod, float* scratch) {
-                        const float s = warp_tree(prod);
-                        if (lane == 0) scratch[warp] = s;
+                const unsigned wp = smem_u32(vp + br * kSlot), wr = smem_u32(vr + br * kSlot);  // this row's window: padded blocks br .. br+2
+                const unsigned own_p = smem_u32(vp + own), own_r = smem_u32(vr + own);
+                const unsigned sA = smem_u32(scratchA), sB = smem_u32(scratchB);
+                const unsigned my_prod = smem_u32(prod + tid), row_prod = smem_u32(prod + 32 * warp);
+                // dot, phase 1 (before the CTA barrier): the warp's partial sum -> scratch[warp]
+                auto dot_partial = [&](float term, unsigned scratch) {
+#if GATO_PCG_DOT_STAGE1 == 1
+                        sts32(my_prod, term);
+                        __syncwarp();
+                        if (lane == 0) sts32(scratch + 4u * warp, tree32(row_prod));
+                        __syncwarp();  // the row is free for the next product
+#else
+                        const float sum = warp_tree(term);
+                        if (lane == 0) sts32(scratch + 4u * warp, sum);
+#endif
+                };
+                // dot, phase 2 (after it): lane 0 folds the per-warp sums, the warp takes its value
+                auto dot_final = [&](unsigned scratch) -> float {
+#if GATO_PCG_DOT_STAGE2 == 1
+                        float v = 0.0f;
+                        if (lane == 0) v = tree16(scratch);
+                        return __shfl_sync(0xffffffffu, v, 0);
+#else
+                        return tree16(scratch);
+#endif
                 };
                 if (!skip) {
                         float x_i = in_vec ? lam[tid] : 0.0f;
-                        if (in_vec) vp[own] = x_i;  // vp temporarily holds x for r = gamma - S x
+                        if (in_vec) sts32(own_p, x_i);  // vp temporarily holds x for r = gamma - S x
                         __syncthreads();
                         float r_i = 0.0f, p_i = 0.0f, z_i = 0.0f;
                         {
                                 const float sx = row_ok ? matvec_packed<NX>(S2, wp) : 0.0f;
                                 r_i = in_vec ? (gam[tid] - sx) : 0.0f;
-                                if (in_vec) vr[own] = r_i;
+                                if (in_vec) sts32(own_r, r_i);
                         }
                         __syncthreads();
                         z_i = row_ok ? matvec_packed<NX>(P2, wr) : 0.0f;
                         p_i = z_i;
-                        if (in_vec) vp[own] = p_i;
-                        dot_partial(fmaf(r_i, z_i, 0.0f), scratchA);
+                        if (in_vec) sts32(own_p, p_i);
+                        dot_partial(fmaf(r_i, z_i, 0.0f), sA);
                         __syncthreads();
-                        float rho = dot_final16(scratchA);
+                        float rho = dot_final(sA);
                         if (!(fabsf(rho) < abs_tol)) {
                                 const float rho_init = fabsf(rho);
                                 for (int itn = 0; itn < c.max_pcg; itn++) {
                                         iters++;
                                         const float Ap_i = row_ok ? matvec_packed<NX>(S2, wp) : 0.0f;
-                                        dot_partial(fmaf(p_i, Ap_i, 0.0f), scratchB);
+                                        dot_partial(fmaf(p_i, Ap_i, 0.0f), sB);
                                         __syncthreads();
-                                        const float alpha = rho / dot_final16(scratchB);
+                                        const float alpha = rho / dot_final(sB);
                                         x_i = fmaf(alpha, p_i, x_i);
                                         r_i = fmaf(-alpha, Ap_i, r_i);
-                                        if (in_vec) vr[own] = r_i;
+                                        if (in_vec) sts32(own_r, r_i);
                                         __syncthreads();
                                         z_i = row_ok ? matvec_packed<NX>(P2, wr) : 0.0f;
-                                        dot_partial(fmaf(r_i, z_i, 0.0f), scratchA);
+                                        dot_partial(fmaf(r_i, z_i, 0.0f), sA);
                                         __syncthreads();
-                                        const float rho_new = dot_final16(scratchA);
+                                        const float rho_new = dot_final(sA);
                                         if (fabsf(rho_new) < fmaf(eps, rho_init, abs_tol)) break;
                                         const float beta = rho_new / rho;
                                         rho = rho_new;
                                         p_i = fmaf(beta, p_i, z_i);
-                                        if (in_vec) vp[own] = p_i;
+                                        if (in_vec) sts32(own_p, p_i);
                                         __syncthreads();
                                 }
                                 if (in_vec) lam[tid] = x_i;
@@ -670,3 +712,5 @@ __global__ void __launch_bounds__(1024, 1) k_pcg_stream(Ctx c)
                 dz_phase<NX, NU>(c, b, N, n, warp, lane, nwarps, dzbuf, c.lambda + (size_t)b * n, c.A + kb * NX2, c.Bm + kb * NX * NU, c.Qinv + kb * NX2, c.Rinv + kb * NU * NU, c.q + kb * NX,
                                  c.r + kb * NU);
 }
+
+}  // namespace gato

@@ -4,7 +4,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "bsqp_kernels.cuh"
+#include "bsqp_ctx.cuh"
+#include "pcg_layout.h"
+#include "rbd.cuh"  // plant tags (Iiwa14, Indy7)
 
 namespace gato {
 

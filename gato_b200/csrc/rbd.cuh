@@ -22,13 +22,9 @@
 #include <cstdint>
 #include <type_traits>
 
+#include "costs.h"
+#include "sfor.h"
 #include "robot_model_data.h"
-
-#if defined(__CUDACC__)
-#define GATO_HD __host__ __device__ __forceinline__
-#else
-#define GATO_HD inline __attribute__((always_inline))
-#endif
 
 namespace gato {
 
@@ -47,23 +43,6 @@ GATO_HD float g_sin(float x) { return sinf(x); }
 GATO_HD float g_cos(float x) { return cosf(x); }
 GATO_HD float g_log(float x) { return logf(x); }
 #endif
-
-template<int I, int N, class F>
-GATO_HD void sfor(F&& f)
-{
-        if constexpr (I < N) {
-                f(std::integral_constant<int, I>{});
-                sfor<I + 1, N>(f);
-        }
-}
-template<int I, int N, class F>
-GATO_HD void sfor_down(F&& f)  // I = N-1 ... 0
-{
-        if constexpr (N > I) {
-                f(std::integral_constant<int, N - 1>{});
-                sfor_down<I, N - 1>(f);
-        }
-}
 
 constexpr float kGravity = 9.81f;  // iiwa14_plant.cuh:25-28
 
@@ -699,10 +678,6 @@ struct Rbd {
                 if (amax < eps) amax = eps;
                 return 1.0f / (amin * amin) + 1.0f / (amax * amax);
         }
-};
-
-struct Costs {
-        float q_cost, qd_cost, u_cost, N_cost, q_lim_cost, vel_lim_cost, ctrl_lim_cost;
 };
 
 // block::reduce's halving tree with odd carry (linalg.cuh:329-353), evaluated by one thread on registers

@@ -1,5 +1,6 @@
 // body of the k_kkt translation units; GATO_TU_PLANT selects the plant
 #include "launchers.h"
+#include "bsqp_kkt_kernels.cuh"
 namespace gato {
 template<>
 void enqueue_kkt<GATO_TU_PLANT>(const Ctx& c, cudaStream_t st)

@@ -1,5 +1,7 @@
 // body of the Schur / PCG translation units; GATO_TU_PLANT selects the plant
 #include "launchers.h"
+#include "bsqp_linalg_kernels.cuh"
+#include "bsqp_pcg_kernels.cuh"
 namespace gato {
 template<>
 size_t schur_smem_bytes<GATO_TU_PLANT>()

@@ -1,5 +1,6 @@
 // body of the merit / line-search / sim_forward translation units; GATO_TU_PLANT selects the plant
 #include "launchers.h"
+#include "bsqp_merit_kernels.cuh"
 namespace gato {
 namespace {
 inline int merit_threads(int na, int N)
