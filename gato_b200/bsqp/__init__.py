@@ -108,6 +108,19 @@ def _make_class(plant, N, B):
         def sim_forward(self, xk, uk, dt):
             return self._s.sim_forward(self._arr(xk, self._d["nx"], "xk"), self._arr(uk, self._d["nu"], "uk"), float(dt))
 
+        def ee_pos(self, q):
+            """Extension: end-effector xyz of joint configurations q[n][nq] by the solver's own forward kinematics (what interface.py:212-214
+            asks pinocchio for in the reference)."""
+            return self._s.ee_pos(q)
+
+        def set_kkt_residual_log(self, enabled=True):
+            """Extension: with the log on, `kkt_residuals()` returns the per-iteration KKT residual norms
+            (q_max, c_max) the reference computes and discards (bsqp.cuh:149-150)."""
+            self._s.set_kkt_residual_log(enabled)
+
+        def kkt_residuals(self):
+            return self._s.kkt_residuals()
+
     _BSQP.__name__ = _BSQP.__qualname__ = f"BSQP_{B}_float"
     return _BSQP
 

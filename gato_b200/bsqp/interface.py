@@ -64,6 +64,9 @@ class BSQP:
         st["best_merit_per_iter_normalized"] = st["best_merit_per_iter"] / denom if (denom and st["best_merit_per_iter"].size) else st["best_merit_per_iter"]
         return self.XU_B, result["sqp_time_us"]
 
+    def ee_pos(self, q):  # interface.py:212-214 (pinocchio forward kinematics there; the solver's own kinematics here)
+        return self.solver.ee_pos(np.asarray(q, dtype=np.float32).reshape(1, self.nq))[0]
+
     def reset(self):  # interface.py:216-219
         self.reset_dual()
         self.set_f_ext_B(np.zeros((self.batch_size, 6)))

@@ -49,6 +49,7 @@ struct Ctx {
         int*         conv;        // [B] "PCG performed 0 iterations" flags (bsqp.cuh:153)
         unsigned*    num_solved;  // [max_sqp_iters] #flagged solves after the PCG of iteration i
         int*         pcg_log;     // [max_sqp_iters][B]
+        unsigned *   kkt_qmax, *kkt_cmax;  // optional [max_sqp_iters][B]: max |KKT residual q|, max |c| per solve as float bits (bsqp.cuh:149-150); may be null
         float *      ls_merit_log, *ls_step_log;  // [max_sqp_iters][B]
 };
 

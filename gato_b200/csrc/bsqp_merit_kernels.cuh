@@ -173,4 +173,20 @@ __global__ void __launch_bounds__(64) k_sim_forward(int B, float* xkp1, const fl
         });
 }
 
+// =====================================================================================================
+// k_ee_pos: thread per joint configuration -- the forward kinematics the cost uses (end_effector_pose_inner, iiwa14_grid.cuh:2596), exposed for
+// the Python wrapper's ee_pos (python/bsqp/interface.py:212-214, which calls pinocchio there)
+// =====================================================================================================
+template<class P>
+__global__ void __launch_bounds__(64) k_ee_pos(int n, const float* q, float* ee)
+{
+        constexpr int NQ = P::NQ;
+        const int     i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n) return;
+        float qi[NQ], e[3];
+        sfor<0, NQ>([&](auto ic) { qi[ic] = q[(size_t)i * NQ + ic]; });
+        Rbd<P>::ee_pos(qi, e);
+        sfor<0, 3>([&](auto ic) { ee[(size_t)i * 3 + ic] = e[ic]; });
+}
+
 }  // namespace gato

@@ -111,6 +111,17 @@ __device__ __forceinline__ void dz_phase(const Ctx& c, int b, int N, int n, int 
                                 c.r[(kb + k) * NU + x] = 0.0f;
                         }
                 }
+                if (c.kkt_qmax) {
+                        // telemetry the reference computes on the host and discards (bsqp.cuh:149-150): max |q residual| and max |c| over the solve's
+                        // state entries; non-negative floats order like their bit patterns, so the maximum is taken on the bits
+                        const bool     st = lane < NX;
+                        const unsigned mq = __reduce_max_sync(0xffffffffu, st ? __float_as_uint(fabsf(wbuf[lane])) : 0u);
+                        const unsigned mc = __reduce_max_sync(0xffffffffu, st ? __float_as_uint(fabsf(c.c[(kb + k) * NX + lane])) : 0u);
+                        if (lane == 0) {
+                                atomicMax(&c.kkt_qmax[(size_t)c.it * c.B + b], mq);
+                                atomicMax(&c.kkt_cmax[(size_t)c.it * c.B + b], mc);
+                        }
+                }
         }
 }
 

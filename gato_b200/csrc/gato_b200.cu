@@ -91,6 +91,11 @@ struct gato_solver {
         DevArr<float>    Q, R, q, r, A, Bm, c, Qinv, Rinv, S, Pinv, Pmain, gamma, lambda, dz;
         DevArr<float>    rho, drho, mu, pcg_tol, fext, merit, merit_cur, merit0, step, ls_merit_log, ls_step_log;
         DevArr<int>      conv, pcg_log;
+        // optional KKT residual telemetry (gato_set_kkt_residual_log): max |q residual| / max |c| per solve and iteration, as float bits
+        DevArr<unsigned> kkt_qmax, kkt_cmax;
+        float *          h_kkt_qmax = nullptr, *h_kkt_cmax = nullptr;
+        bool             kkt_log = false;
+        DevArr<float>    ee_q, ee_out;  // staging of gato_ee_pos
         DevArr<unsigned> num_solved;
         DevArr<float>    st_xu, st_xs, st_ref, st_xkp1, st_xk, st_uk;  // staging for *_host calls
         // reset defaults of rho / drho (bsqp.cuh:48-58, 84-87, 189), resident on the device so that resets are device-to-device copies
@@ -161,6 +166,7 @@ Ctx make_ctx(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref,
         c.S = s->S.p, c.Pinv = s->Pinv.p, c.Pmain = s->Pmain.p, c.gamma = s->gamma.p, c.lambda = s->lambda.p, c.dz = s->dz.p;
         c.rho = s->rho.p, c.drho = s->drho.p, c.merit = s->merit.p, c.merit_cur = s->merit_cur.p, c.step = s->step.p;
         c.mu = s->mu.p, c.pcg_tol = s->pcg_tol.p;
+        c.kkt_qmax = s->kkt_log ? s->kkt_qmax.p : nullptr, c.kkt_cmax = s->kkt_log ? s->kkt_cmax.p : nullptr;
         c.conv = s->conv.p, c.num_solved = s->num_solved.p, c.pcg_log = s->pcg_log.p, c.ls_merit_log = s->ls_merit_log.p, c.ls_step_log = s->ls_step_log.p;
         return c;
 }
@@ -217,6 +223,10 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
         CUDA_TRY(s, cudaMemsetAsync(s->conv.p, 0, sizeof(int) * B, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->num_solved.p, 0, sizeof(unsigned) * s->max_it, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->pcg_log.p, 0, sizeof(int) * (size_t)s->max_it * B, s->stream));
+        if (s->kkt_log) {
+                CUDA_TRY(s, cudaMemsetAsync(s->kkt_qmax.p, 0, sizeof(unsigned) * (size_t)s->max_it * B, s->stream));
+                CUDA_TRY(s, cudaMemsetAsync(s->kkt_cmax.p, 0, sizeof(unsigned) * (size_t)s->max_it * B, s->stream));
+        }
         // initial merit (dz = 0, alpha = 1)  bsqp.cuh:116-118.  Nothing before the first line search depends on it, so it is enqueued on a
         // side stream and joined there (with the per-kernel timing on it stays in line so that the event brackets remain meaningful).
         c.flags = F_MERIT | F_ZERO_DZ;
@@ -263,6 +273,10 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
         CUDA_TRY(s, cudaMemcpyAsync(s->h_conv, s->conv.p, sizeof(int) * B, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(s, cudaMemcpyAsync(s->h_final, s->merit_cur.p, sizeof(float) * B, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(s, cudaMemcpyAsync(s->h_initial, s->merit0.p, sizeof(float) * B, cudaMemcpyDeviceToHost, s->stream));
+        if (s->kkt_log) {
+                CUDA_TRY(s, cudaMemcpyAsync(s->h_kkt_qmax, s->kkt_qmax.p, sizeof(unsigned) * (size_t)s->max_it * B, cudaMemcpyDeviceToHost, s->stream));
+                CUDA_TRY(s, cudaMemcpyAsync(s->h_kkt_cmax, s->kkt_cmax.p, sizeof(unsigned) * (size_t)s->max_it * B, cudaMemcpyDeviceToHost, s->stream));
+        }
         // drho is reset after every solve (bsqp.cuh:189); lambda and rho persist
         CUDA_TRY(s, cudaMemcpyAsync(s->drho.p, s->drho_init.p, sizeof(float) * B, cudaMemcpyDeviceToDevice, s->stream));
         return GATO_OK;
@@ -456,7 +470,9 @@ void gato_destroy(gato_solver* s)
         for (auto* a : {&s->Q, &s->R, &s->q, &s->r, &s->A, &s->Bm, &s->c, &s->Qinv, &s->Rinv, &s->S, &s->Pinv, &s->Pmain, &s->gamma, &s->lambda, &s->dz, &s->rho, &s->drho, &s->rho_init, &s->drho_init, &s->mu, &s->pcg_tol, &s->fext,
                         &s->merit, &s->merit_cur, &s->merit0, &s->step, &s->ls_merit_log, &s->ls_step_log, &s->st_xu, &s->st_xs, &s->st_ref, &s->st_xkp1, &s->st_xk, &s->st_uk})
                 a->release();
-        s->conv.release(), s->pcg_log.release(), s->num_solved.release();
+        s->conv.release(), s->pcg_log.release(), s->num_solved.release(), s->kkt_qmax.release(), s->kkt_cmax.release(), s->ee_q.release(), s->ee_out.release();
+        if (s->h_kkt_qmax) cudaFreeHost(s->h_kkt_qmax);
+        if (s->h_kkt_cmax) cudaFreeHost(s->h_kkt_cmax);
         for (void* p : {(void*)s->h_pcg_log, (void*)s->h_conv, (void*)s->h_num_solved, (void*)s->h_ls_merit, (void*)s->h_ls_step, (void*)s->h_final, (void*)s->h_initial})
                 if (p) cudaFreeHost(p);
         for (auto* a : {&s->mpc_xu, &s->mpc_xs, &s->mpc_ref, &s->mpc_off, &s->mpc_in, &s->mpc_xnext}) a->release();
@@ -591,6 +607,68 @@ int gato_get_merits(gato_solver* s, float* h_final, float* h_initial)
         // ordered after everything enqueued on the solver's (non-blocking) stream
         if (h_final) CUDA_TRY(s, cudaMemcpyAsync(h_final, s->merit_cur.p, sizeof(float) * s->B, cudaMemcpyDeviceToHost, s->stream));
         if (h_initial) CUDA_TRY(s, cudaMemcpyAsync(h_initial, s->merit0.p, sizeof(float) * s->B, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        return GATO_OK;
+}
+
+int gato_set_kkt_residual_log(gato_solver* s, int enable)
+{
+        if (!s) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        if (s->pending) {
+                s->err = "gato_set_kkt_residual_log: a solve is still pending (call gato_solve_wait first)";
+                return GATO_ERR_ARG;
+        }
+        if (enable && !s->kkt_qmax.p) {
+                const size_t n = (size_t)s->max_it * s->B;
+                CUDA_TRY(s, s->kkt_qmax.alloc(n));
+                CUDA_TRY(s, s->kkt_cmax.alloc(n));
+                CUDA_TRY(s, cudaMallocHost((void**)&s->h_kkt_qmax, sizeof(float) * n));
+                CUDA_TRY(s, cudaMallocHost((void**)&s->h_kkt_cmax, sizeof(float) * n));
+        }
+        s->kkt_log = enable != 0;
+        return GATO_OK;
+}
+
+int gato_get_kkt_residuals(gato_solver* s, float* h_q_max, float* h_c_max)
+{
+        if (!s) return GATO_ERR_ARG;
+        if (s->pending || !s->kkt_log) {
+                s->err = s->pending ? "gato_get_kkt_residuals: a solve is still pending" : "gato_get_kkt_residuals: enable the log with gato_set_kkt_residual_log first";
+                return GATO_ERR_ARG;
+        }
+        // rows of the last completed solve: one per PCG solve performed
+        const float thresh = (float)(uint32_t)s->B * s->prm.solve_ratio;
+        int         n_pcg = s->n_it;
+        for (int i = 0; i < s->n_it; i++)
+                if ((float)s->h_num_solved[i] >= thresh) {
+                        n_pcg = i + 1;
+                        break;
+                }
+        const size_t n = (size_t)n_pcg * s->B;
+        if (h_q_max) memcpy(h_q_max, s->h_kkt_qmax, sizeof(float) * n);  // the maxima were taken on the bit patterns of non-negative floats
+        if (h_c_max) memcpy(h_c_max, s->h_kkt_cmax, sizeof(float) * n);
+        return n_pcg;
+}
+
+int gato_ee_pos(gato_solver* s, const float* h_q, int n, float* h_ee)
+{
+        if (!s || !h_q || !h_ee || n < 1) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        const int nq = s->d.nq;
+        if (s->ee_q.n < (size_t)n * nq) {
+                s->ee_q.release(), s->ee_out.release();
+                CUDA_TRY(s, s->ee_q.alloc((size_t)n * nq));
+                CUDA_TRY(s, s->ee_out.alloc((size_t)n * 3));
+        }
+        CUDA_TRY(s, cudaMemcpyAsync(s->ee_q.p, h_q, sizeof(float) * (size_t)n * nq, cudaMemcpyHostToDevice, s->stream));
+        if (s->plant == GATO_PLANT_IIWA14)
+                enqueue_ee_pos<Iiwa14>(n, s->ee_q.p, s->ee_out.p, s->stream);
+        else
+                enqueue_ee_pos<Indy7>(n, s->ee_q.p, s->ee_out.p, s->stream);
+        s->launches++;
+        CUDA_TRY(s, cudaGetLastError());
+        CUDA_TRY(s, cudaMemcpyAsync(h_ee, s->ee_out.p, sizeof(float) * (size_t)n * 3, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(s, cudaStreamSynchronize(s->stream));
         return GATO_OK;
 }

@@ -30,6 +30,9 @@ size_t schur_smem_bytes();
 // num_alphas = 1 (initial / final merit) or kNumAlphas (merit + line search)
 template<class P>
 void enqueue_merit(const Ctx& c, int num_alphas, cudaStream_t st);
+// end-effector position (forward kinematics) of n joint configurations: q[n][nq] -> ee[n][3]
+template<class P>
+void enqueue_ee_pos(int n, const float* q, float* ee, cudaStream_t st);
 template<class P>
 void enqueue_sim_forward(int B, float* xkp1, const float* xk, const float* uk, const float* fext, float dt, cudaStream_t st);
 

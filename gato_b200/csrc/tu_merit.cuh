@@ -27,6 +27,11 @@ void enqueue_merit<GATO_TU_PLANT>(const Ctx& c, int na, cudaStream_t st)
                 k_merit_ls<GATO_TU_PLANT, kNumAlphas><<<c.B, merit_threads(kNumAlphas, c.N), smem, st>>>(c);
 }
 template<>
+void enqueue_ee_pos<GATO_TU_PLANT>(int n, const float* q, float* ee, cudaStream_t st)
+{
+        k_ee_pos<GATO_TU_PLANT><<<(n + 63) / 64, 64, 0, st>>>(n, q, ee);
+}
+template<>
 void enqueue_sim_forward<GATO_TU_PLANT>(int B, float* xkp1, const float* xk, const float* uk, const float* fext, float dt, cudaStream_t st)
 {
         const int T = 64, G = (B + T - 1) / T;

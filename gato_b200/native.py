@@ -85,6 +85,10 @@ def load():
     lib.gato_get_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.gato_get_launch_times.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]
     lib.gato_get_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    if hasattr(lib, "gato_ee_pos"):
+        lib.gato_ee_pos.argtypes = [vp, f32p, C.c_int, f32p]
+        lib.gato_set_kkt_residual_log.argtypes = [vp, C.c_int]
+        lib.gato_get_kkt_residuals.argtypes = [vp, f32p, f32p]
     if hasattr(lib, "gato_measure_fp32_peak"):  # absent from older builds loaded through GATO_B200_LIB for A/B runs
         lib.gato_measure_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     lead = [C.c_int, C.c_int, C.c_int]
@@ -199,6 +203,25 @@ class Solver:
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._check(self.lib.gato_get_device_pointers(self.h, C.byref(a), C.byref(b), C.byref(c)), "gato_get_device_pointers")
         return a.value, b.value, c.value
+
+    def ee_pos(self, q):
+        """End-effector xyz of joint configurations q[n][nq] (or [nq]) by the solver's forward kinematics."""
+        q = _f(q).reshape(-1, self.d["nq"])
+        out = np.zeros((q.shape[0], 3), np.float32)
+        self._check(self.lib.gato_ee_pos(self.h, q.reshape(-1), q.shape[0], out.reshape(-1)), "gato_ee_pos")
+        return out
+
+    def set_kkt_residual_log(self, enable=True):
+        self._check(self.lib.gato_set_kkt_residual_log(self.h, int(bool(enable))), "gato_set_kkt_residual_log")
+
+    def kkt_residuals(self):
+        """(q_max[n_pcg][B], c_max[n_pcg][B]) of the last completed solve (needs set_kkt_residual_log(True) before it)."""
+        cap = max(int(self.params["max_sqp_iters"]), 1) * self.B
+        qm, cm = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        n = self.lib.gato_get_kkt_residuals(self.h, qm, cm)
+        if n < 0:
+            self._check(n, "gato_get_kkt_residuals")
+        return qm[: n * self.B].reshape(n, self.B), cm[: n * self.B].reshape(n, self.B)
 
     def sim_forward(self, xk, uk, dt):
         out = np.zeros((self.B, self.d["nx"]), np.float32)

@@ -121,6 +121,16 @@ int gato_get_kernel_times(gato_solver* s, float* total_ms /* [5] */, int* launch
 /* every launch of the last completed solve in launch order: class id and duration; returns the number of launches written (<= cap) or < 0 */
 int gato_get_launch_times(gato_solver* s, int* kernel_class, float* ms, int cap);
 
+/* End-effector position of n joint configurations by the solver's own forward kinematics (the one its tracking cost uses):
+ * q[n][nq] -> ee[n][3].  Replaces the pinocchio call of python/bsqp/interface.py:212-214 (BSQP.ee_pos). */
+int gato_ee_pos(gato_solver* s, const float* h_q, int n, float* h_ee);
+/* Optional telemetry: the KKT residual norms the reference computes on the host in every SQP iteration and then discards
+ * (gato/bsqp/bsqp.cuh:149-150): q_max[i][b] = max |q residual| and c_max[i][b] = max |c| over the state entries of solve b after the primal
+ * step of iteration i.  Off by default (no cost); gato_get_kkt_residuals copies [n_pcg][B] floats each for the last completed solve and
+ * returns n_pcg (or a negative status). */
+int gato_set_kkt_residual_log(gato_solver* s, int enable);
+int gato_get_kkt_residuals(gato_solver* s, float* h_q_max, float* h_c_max);
+
 /* Measured FP32 CUDA-core peak of `device` in TFLOP/s (the denominator of the FP32 roofline fractions bench.py
  * reports; MEASURED_PEAKS.json has no FP32 number): a register-resident fused-multiply-add loop at full occupancy, packed = 0 scalar FFMA,
  * packed = 1 Blackwell's two-wide FFMA2 (what the linear-algebra kernels of this library issue).  Measurement aid, not on the solve path. */

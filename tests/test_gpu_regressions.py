@@ -94,3 +94,46 @@ def test_get_merits_is_ordered_and_rejects_pending_solves():
     assert lib.gato_get_merits(s.h, vp(fin), vp(ini)) == -1 and b"pending" in lib.gato_last_error(s.h)
     s.solve_wait()
     assert lib.gato_get_merits(s.h, vp(fin), vp(ini)) == 0
+
+
+@pytest.mark.parametrize("plant", ["iiwa14", "indy7"])
+def test_ee_pos_matches_the_oracle_kinematics(backends, plant):
+    """gato_ee_pos / BSQP.ee_pos (reference python/bsqp/interface.py:212-214): the solver's forward kinematics, bit-for-bit the oracle's
+    end-effector position (the one the tracking cost is built on)."""
+    from gato_b200.bsqp.interface import BSQP
+
+    o, g = backends(plant, 8)
+    nq = o.d["nq"]
+    rng = np.random.default_rng(3)
+    q = rng.uniform(-2.5, 2.5, (37, nq)).astype(np.float32)
+    x = np.concatenate([q, np.zeros_like(q)], 1)
+    want = o.dyn_dump(x, np.zeros((37, nq), np.float32), np.zeros((37, 6), np.float32))["ee"][:, :3]
+    w = make_config(1 if plant == "iiwa14" else 3, B=2, N=8)
+    got = g.solver(2, w["params"]).ee_pos(q)
+    assert n_mismatch(got, want) == 0
+    b = BSQP(None, 2, 8, 0.01, plant_type=plant)
+    assert n_mismatch(b.ee_pos(q[5]), want[5]) == 0
+
+
+def test_kkt_residual_log(backends):
+    """Optional q_max / c_max outputs (the norms bsqp.cuh:149-150 computes and discards): equal to max |.| of the oracle's stage outputs, and
+    switching the log on does not change the solve."""
+    o, g = backends("iiwa14", 8)
+    B = 5
+    w = make_config(1, B=B)
+    p = dict(w["params"], max_sqp_iters=1)
+    xu = w["xu"] + np.random.default_rng(2).normal(0, 0.05, w["xu"].shape).astype(np.float32)
+    plain = g.solver(B, p).solve(xu, w["xs"], w["ref"], w["dt"])
+    s = g.solver(B, p)
+    s.set_kkt_residual_log(True)
+    r = s.solve(xu, w["xs"], w["ref"], w["dt"])
+    assert n_mismatch(r["XU"], plain["XU"]) == 0
+    qm, cm = s.kkt_residuals()
+    assert qm.shape == (1, B) and cm.shape == (1, B)
+    # the same iteration through the oracle's stages
+    kk = o.stage_kkt(B, xu, w["xs"], w["ref"], np.zeros((B, 6), np.float32), w["dt"], p)
+    sc = o.stage_schur(B, kk, np.full(B, p["rho"], np.float32))
+    lam, _ = o.stage_pcg(B, sc["S"], sc["Pinv"], sc["gamma"], np.zeros((B, o.d["vecp"]), np.float32), np.full(B, p["pcg_tol"], np.float32), int(p["max_pcg_iters"]))
+    _, qres, _ = o.stage_dz(B, lam, sc["Qinv"], sc["Rinv"], kk["q"], kk["r"], kk["A"], kk["Bm"])
+    assert n_mismatch(qm[0], np.abs(qres.reshape(B, -1)).max(1)) == 0
+    assert n_mismatch(cm[0], np.abs(kk["c"].reshape(B, -1)).max(1)) == 0
