@@ -72,8 +72,10 @@ struct gato_solver {
         std::string  err;
         long         launches = 0;
         // closed-loop MPC step state (allocated on first use)
-        DevArr<float>  mpc_xu, mpc_xs, mpc_ref, mpc_off, mpc_in, mpc_xnext;
-        DevArr<double> mpc_err;
+        DevArr<float>  mpc_xu, mpc_xs, mpc_ref, mpc_off, mpc_in, mpc_xnext, mpc_rec;
+        DevArr<double> mpc_err, mpc_gerr;
+        double*        h_mpc_gerr = nullptr;  // pinned: the global winner's error
+        bool           mpc_scored = false;
         DevArr<int>    mpc_best;
         bool           mpc_has_off = false;
         float*         h_mpc_in = nullptr;    // pinned: x_curr | ref window | x_last | u_last
@@ -475,9 +477,9 @@ void gato_destroy(gato_solver* s)
         if (s->h_kkt_cmax) cudaFreeHost(s->h_kkt_cmax);
         for (void* p : {(void*)s->h_pcg_log, (void*)s->h_conv, (void*)s->h_num_solved, (void*)s->h_ls_merit, (void*)s->h_ls_step, (void*)s->h_final, (void*)s->h_initial})
                 if (p) cudaFreeHost(p);
-        for (auto* a : {&s->mpc_xu, &s->mpc_xs, &s->mpc_ref, &s->mpc_off, &s->mpc_in, &s->mpc_xnext}) a->release();
-        s->mpc_err.release(), s->mpc_best.release();
-        for (void* p : {(void*)s->h_mpc_in, (void*)s->h_mpc_best, (void*)s->h_mpc_err, (void*)s->h_mpc_id})
+        for (auto* a : {&s->mpc_xu, &s->mpc_xs, &s->mpc_ref, &s->mpc_off, &s->mpc_in, &s->mpc_xnext, &s->mpc_rec}) a->release();
+        s->mpc_err.release(), s->mpc_best.release(), s->mpc_gerr.release();
+        for (void* p : {(void*)s->h_mpc_in, (void*)s->h_mpc_best, (void*)s->h_mpc_err, (void*)s->h_mpc_id, (void*)s->h_mpc_gerr})
                 if (p) cudaFreeHost(p);
         for (cudaEvent_t e : s->tick_ev) cudaEventDestroy(e);
         if (s->side) cudaStreamSynchronize(s->side), cudaStreamDestroy(s->side);
@@ -770,17 +772,47 @@ __global__ void k_mpc_score(int B, int nx, const float* __restrict__ xnext, cons
                 best[0] = id < 0 ? 0 : id;
         }
 }
-__global__ void k_mpc_adopt(int B, int traj, float* xu, const int* best, float* best_out)
+// Winner record of one shard (floats): [0..1] error (double) | [2] local id (int) | [3] unused | [4 .. 4+traj) the winner's trajectory
+__host__ __device__ inline int mpc_record_floats(int traj) { return (4 + traj + 3) / 4 * 4; }
+__global__ void k_mpc_record(int traj, const float* __restrict__ xu, const double* __restrict__ err, const int* __restrict__ best, float* rec)
 {
-        const int    b = blockIdx.x, src = best[0];
-        const float* s = xu + (size_t)src * traj;
-        if (b == B) {  // extra block: export the winner
-                for (int i = threadIdx.x; i < traj; i += blockDim.x) best_out[i] = s[i];
+        const int id = best[0];
+        if (threadIdx.x == 0) {
+                *reinterpret_cast<double*>(rec) = err[id];
+                reinterpret_cast<int*>(rec)[2] = id;
+                rec[3] = 0.0f;
+        }
+        const float* src = xu + (size_t)id * traj;
+        for (int i = threadIdx.x; i < traj; i += blockDim.x) rec[4 + i] = src[i];
+}
+// Global winner among n shard records (np.argmin over the concatenated error vector: the first minimum, the first NaN beats every number;
+// each record already is its shard's first minimum, so ties go to the lower shard), then XU[:] = winner (mpc_controller.py:252-253).
+// Block B exports the winner: trajectory, global id (= shard * id_stride + local id) and error.
+__global__ void k_mpc_select_adopt(int B, int traj, float* xu, const float* __restrict__ recs, int n, int stride, int id_stride, float* best_out, int* gid_out, double* gerr_out)
+{
+        __shared__ int s_win;
+        if (threadIdx.x == 0) {
+                int    win = 0;
+                double v = *reinterpret_cast<const double*>(recs);
+                for (int r = 1; r < n; r++) {
+                        const double x = *reinterpret_cast<const double*>(recs + (size_t)r * stride);
+                        if (v == v && (x != x || x < v)) v = x, win = r;  // v is NaN: nothing later can win
+                }
+                s_win = win;
+        }
+        __syncthreads();
+        const float* rec = recs + (size_t)s_win * stride;
+        const int    b = blockIdx.x;
+        if (b == B) {
+                for (int i = threadIdx.x; i < traj; i += blockDim.x) best_out[i] = rec[4 + i];
+                if (threadIdx.x == 0) {
+                        gid_out[0] = s_win * id_stride + reinterpret_cast<const int*>(rec)[2];
+                        gerr_out[0] = *reinterpret_cast<const double*>(rec);
+                }
                 return;
         }
-        if (b == src) return;
         float* d = xu + (size_t)b * traj;
-        for (int i = threadIdx.x; i < traj; i += blockDim.x) d[i] = s[i];
+        for (int i = threadIdx.x; i < traj; i += blockDim.x) d[i] = rec[4 + i];
 }
 
 int mpc_ensure(gato_solver* s)
@@ -795,11 +827,14 @@ int mpc_ensure(gato_solver* s)
         CUDA_TRY(s, s->mpc_in.alloc(2 * d.nx + 6 * d.N + d.nu));
         CUDA_TRY(s, s->mpc_xnext.alloc(B * d.nx + d.traj));  // x_next batch, then the exported winner
         CUDA_TRY(s, s->mpc_err.alloc(B));
-        CUDA_TRY(s, s->mpc_best.alloc(1));
+        CUDA_TRY(s, s->mpc_best.alloc(2));  // [0] local winner, [1] global winner id
+        CUDA_TRY(s, s->mpc_rec.alloc(mpc_record_floats(d.traj)));
+        CUDA_TRY(s, s->mpc_gerr.alloc(1));
         CUDA_TRY(s, cudaMallocHost((void**)&s->h_mpc_in, sizeof(float) * (2 * d.nx + 6 * d.N + d.nu)));
         CUDA_TRY(s, cudaMallocHost((void**)&s->h_mpc_best, sizeof(float) * d.traj));
         CUDA_TRY(s, cudaMallocHost((void**)&s->h_mpc_err, sizeof(double) * B));
         CUDA_TRY(s, cudaMallocHost((void**)&s->h_mpc_id, sizeof(int)));
+        CUDA_TRY(s, cudaMallocHost((void**)&s->h_mpc_gerr, sizeof(double)));
         return GATO_OK;
 }
 }  // namespace
@@ -845,6 +880,86 @@ int gato_mpc_get_warm_start(gato_solver* s, float* h_xu)
         return GATO_OK;
 }
 
+int gato_mpc_record_floats(const gato_solver* s) { return s ? mpc_record_floats(s->d.traj) : GATO_ERR_ARG; }
+int gato_mpc_input_floats(const gato_solver* s) { return s ? 2 * s->d.nx + 6 * s->d.N + s->d.nu : GATO_ERR_ARG; }
+
+int gato_mpc_local_async(gato_solver* s, const float* d_in, int score, float sim_dt, float timestep, int flags, float* d_record)
+{
+        if (!s || !d_in || !d_record) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        if (!s->mpc_xu.p) {
+                s->err = "gato_mpc_step: call gato_mpc_set_warm_start first";
+                return GATO_ERR_ARG;
+        }
+        const Dims& d = s->d;
+        const int   B = s->B;
+        s->t_start = std::chrono::high_resolution_clock::now();
+        CUDA_TRY(s, cudaEventRecord(s->ev0, s->stream));
+        k_mpc_prepare<<<B, 64, 0, s->stream>>>(B, d.nx, d.N, d.traj, d_in, s->mpc_has_off ? s->mpc_off.p : nullptr, s->mpc_xs.p, s->mpc_ref.p, s->mpc_xu.p);
+        s->launches++;
+        if (flags & GATO_MPC_RESET_RHO) {
+                CUDA_TRY(s, cudaMemcpyAsync(s->rho.p, s->rho_init.p, sizeof(float) * B, cudaMemcpyDeviceToDevice, s->stream));
+                CUDA_TRY(s, cudaMemcpyAsync(s->drho.p, s->drho_init.p, sizeof(float) * B, cudaMemcpyDeviceToDevice, s->stream));
+        }
+        if (int rc = dispatch_enqueue(s, s->mpc_xu.p, s->mpc_xs.p, s->mpc_ref.p, timestep)) return rc;
+        if (score) {
+                const float* d_xl = d_in + d.nx + 6 * d.N;
+                if (s->plant == GATO_PLANT_IIWA14)
+                        enqueue_sim_forward<Iiwa14>(B, s->mpc_xnext.p, d_xl, d_xl + d.nx, s->fext.p, sim_dt, s->stream);
+                else
+                        enqueue_sim_forward<Indy7>(B, s->mpc_xnext.p, d_xl, d_xl + d.nx, s->fext.p, sim_dt, s->stream);
+                k_mpc_score<<<1, 256, 0, s->stream>>>(B, d.nx, s->mpc_xnext.p, d_in, s->mpc_err.p, s->mpc_best.p);
+                s->launches += 2;
+        } else {
+                CUDA_TRY(s, cudaMemsetAsync(s->mpc_best.p, 0, sizeof(int), s->stream));
+                CUDA_TRY(s, cudaMemsetAsync(s->mpc_err.p, 0, sizeof(double) * B, s->stream));
+        }
+        k_mpc_record<<<1, 128, 0, s->stream>>>(d.traj, s->mpc_xu.p, s->mpc_err.p, s->mpc_best.p, d_record);
+        s->launches++;
+        CUDA_TRY(s, cudaGetLastError());
+        s->mpc_scored = score != 0;
+        s->pending = true;
+        return GATO_OK;
+}
+
+int gato_mpc_adopt_async(gato_solver* s, const float* d_records, int n_records, int record_stride, int id_stride)
+{
+        if (!s || !d_records || n_records < 1 || record_stride < mpc_record_floats(s->d.traj)) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        const Dims& d = s->d;
+        const int   B = s->B;
+        float*      d_best_out = s->mpc_xnext.p + (size_t)B * d.nx;
+        k_mpc_select_adopt<<<B + 1, 128, 0, s->stream>>>(B, d.traj, s->mpc_xu.p, d_records, n_records, record_stride, id_stride, d_best_out, s->mpc_best.p + 1, s->mpc_gerr.p);
+        s->launches++;
+        CUDA_TRY(s, cudaEventRecord(s->ev1, s->stream));
+        CUDA_TRY(s, cudaGetLastError());
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_mpc_best, d_best_out, sizeof(float) * d.traj, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_mpc_err, s->mpc_err.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_mpc_id, s->mpc_best.p + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->h_mpc_gerr, s->mpc_gerr.p, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        return GATO_OK;
+}
+
+int gato_mpc_wait(gato_solver* s, gato_mpc_out* out, gato_stats* st)
+{
+        if (!s || !out) return GATO_ERR_ARG;
+        if (check_dev(s)) return GATO_ERR_CUDA;
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        s->pending = false;
+        fill_stats(s, st);
+        if (st) {
+                st->solve_time_us = std::chrono::duration<double, std::micro>(std::chrono::high_resolution_clock::now() - s->t_start).count();
+                float ms = 0;
+                CUDA_TRY(s, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+                st->device_time_ms = ms;
+        }
+        out->best_id = *s->h_mpc_id;
+        out->best_error = *s->h_mpc_gerr;
+        out->errors = s->h_mpc_err;
+        out->xu_best = s->h_mpc_best;
+        return GATO_OK;
+}
+
 int gato_mpc_step(gato_solver* s, const float* h_x_curr, const float* h_ref_window, const float* h_x_last, const float* h_u_last, float sim_dt, float timestep, int flags,
                   gato_mpc_out* out, gato_stats* st)
 {
@@ -855,9 +970,8 @@ int gato_mpc_step(gato_solver* s, const float* h_x_curr, const float* h_ref_wind
                 return GATO_ERR_ARG;
         }
         const Dims& d = s->d;
-        const int   B = s->B, nin = 2 * d.nx + 6 * d.N + d.nu;
+        const int   nin = 2 * d.nx + 6 * d.N + d.nu;
         const bool  score = h_x_last != nullptr;
-        s->t_start = std::chrono::high_resolution_clock::now();
         memcpy(s->h_mpc_in, h_x_curr, sizeof(float) * d.nx);
         memcpy(s->h_mpc_in + d.nx, h_ref_window, sizeof(float) * 6 * d.N);
         if (score) {
@@ -865,47 +979,10 @@ int gato_mpc_step(gato_solver* s, const float* h_x_curr, const float* h_ref_wind
                 memcpy(s->h_mpc_in + 2 * d.nx + 6 * d.N, h_u_last, sizeof(float) * d.nu);
         }
         CUDA_TRY(s, cudaMemcpyAsync(s->mpc_in.p, s->h_mpc_in, sizeof(float) * nin, cudaMemcpyHostToDevice, s->stream));
-        CUDA_TRY(s, cudaEventRecord(s->ev0, s->stream));
-        k_mpc_prepare<<<B, 64, 0, s->stream>>>(B, d.nx, d.N, d.traj, s->mpc_in.p, s->mpc_has_off ? s->mpc_off.p : nullptr, s->mpc_xs.p, s->mpc_ref.p, s->mpc_xu.p);
-        s->launches++;
-        if (flags & GATO_MPC_RESET_RHO) {
-                CUDA_TRY(s, cudaMemcpyAsync(s->rho.p, s->rho_init.p, sizeof(float) * B, cudaMemcpyDeviceToDevice, s->stream));
-                CUDA_TRY(s, cudaMemcpyAsync(s->drho.p, s->drho_init.p, sizeof(float) * B, cudaMemcpyDeviceToDevice, s->stream));
-        }
-        if (int rc = dispatch_enqueue(s, s->mpc_xu.p, s->mpc_xs.p, s->mpc_ref.p, timestep)) return rc;
-        float* d_best_out = s->mpc_xnext.p + (size_t)B * d.nx;
-        if (score) {
-                const float* d_xl = s->mpc_in.p + d.nx + 6 * d.N;
-                if (s->plant == GATO_PLANT_IIWA14)
-                        enqueue_sim_forward<Iiwa14>(B, s->mpc_xnext.p, d_xl, d_xl + d.nx, s->fext.p, sim_dt, s->stream);
-                else
-                        enqueue_sim_forward<Indy7>(B, s->mpc_xnext.p, d_xl, d_xl + d.nx, s->fext.p, sim_dt, s->stream);
-                k_mpc_score<<<1, 256, 0, s->stream>>>(B, d.nx, s->mpc_xnext.p, s->mpc_in.p, s->mpc_err.p, s->mpc_best.p);
-                s->launches += 2;
-        } else {
-                CUDA_TRY(s, cudaMemsetAsync(s->mpc_best.p, 0, sizeof(int), s->stream));
-                CUDA_TRY(s, cudaMemsetAsync(s->mpc_err.p, 0, sizeof(double) * B, s->stream));
-        }
-        k_mpc_adopt<<<B + 1, 128, 0, s->stream>>>(B, d.traj, s->mpc_xu.p, s->mpc_best.p, d_best_out);
-        s->launches++;
-        CUDA_TRY(s, cudaEventRecord(s->ev1, s->stream));
-        CUDA_TRY(s, cudaGetLastError());
-        CUDA_TRY(s, cudaMemcpyAsync(s->h_mpc_best, d_best_out, sizeof(float) * d.traj, cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(s, cudaMemcpyAsync(s->h_mpc_err, s->mpc_err.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(s, cudaMemcpyAsync(s->h_mpc_id, s->mpc_best.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-        fill_stats(s, st);
-        if (st) {
-                st->solve_time_us = std::chrono::duration<double, std::micro>(std::chrono::high_resolution_clock::now() - s->t_start).count();
-                float ms = 0;
-                CUDA_TRY(s, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-                st->device_time_ms = ms;
-        }
-        out->best_id = *s->h_mpc_id;
-        out->best_error = s->h_mpc_err[out->best_id];
-        out->errors = s->h_mpc_err;
-        out->xu_best = s->h_mpc_best;
-        return GATO_OK;
+        // one shard: the local winner is the global one
+        if (int rc = gato_mpc_local_async(s, s->mpc_in.p, score ? 1 : 0, sim_dt, timestep, flags, s->mpc_rec.p)) return rc;
+        if (int rc = gato_mpc_adopt_async(s, s->mpc_rec.p, 1, mpc_record_floats(d.traj), s->B)) return rc;
+        return gato_mpc_wait(s, out, st);
 }
 
 // ------------------------------------------------------------------------------------------------

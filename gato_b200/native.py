@@ -85,6 +85,12 @@ def load():
     lib.gato_get_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.gato_get_launch_times.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]
     lib.gato_get_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    if hasattr(lib, "gato_mpc_local_async"):
+        lib.gato_mpc_record_floats.argtypes = [vp]
+        lib.gato_mpc_input_floats.argtypes = [vp]
+        lib.gato_mpc_local_async.argtypes = [vp, vp, C.c_int, C.c_float, C.c_float, C.c_int, vp]
+        lib.gato_mpc_adopt_async.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+        lib.gato_mpc_wait.argtypes = [vp, C.POINTER(GatoMpcOut), C.POINTER(GatoStats)]
     if hasattr(lib, "gato_ee_pos"):
         lib.gato_ee_pos.argtypes = [vp, f32p, C.c_int, f32p]
         lib.gato_set_kkt_residual_log.argtypes = [vp, C.c_int]
@@ -259,6 +265,29 @@ class Solver:
         self._check(self.lib.gato_mpc_step(self.h, x_curr, ref_window, xl, ul, float(sim_dt), float(dt), 1 if reset_rho else 0, C.byref(out), C.byref(st)), "gato_mpc_step")
         res = self._stats(st)
         res["best_id"] = int(out.best_id)
+        res["errors"] = np.ctypeslib.as_array(out.errors, shape=(self.B,)).copy()
+        res["XU_best"] = np.ctypeslib.as_array(out.xu_best, shape=(self.d["traj"],)).copy()
+        return res
+
+    # ---- the same step in its multi-GPU phases (device pointers as ints; everything is enqueued on the solver's stream) ----
+    def mpc_record_floats(self):
+        return int(self.lib.gato_mpc_record_floats(self.h))
+
+    def mpc_input_floats(self):
+        return int(self.lib.gato_mpc_input_floats(self.h))
+
+    def mpc_local_async(self, d_in, score, sim_dt, dt, reset_rho, d_record):
+        self._check(self.lib.gato_mpc_local_async(self.h, d_in, int(bool(score)), float(sim_dt), float(dt), 1 if reset_rho else 0, d_record), "gato_mpc_local_async")
+
+    def mpc_adopt_async(self, d_records, n_records, record_stride, id_stride):
+        self._check(self.lib.gato_mpc_adopt_async(self.h, d_records, int(n_records), int(record_stride), int(id_stride)), "gato_mpc_adopt_async")
+
+    def mpc_wait(self):
+        out, st = GatoMpcOut(), GatoStats()
+        self._check(self.lib.gato_mpc_wait(self.h, C.byref(out), C.byref(st)), "gato_mpc_wait")
+        res = self._stats(st)
+        res["best_id"] = int(out.best_id)
+        res["best_error"] = float(out.best_error)
         res["errors"] = np.ctypeslib.as_array(out.errors, shape=(self.B,)).copy()
         res["XU_best"] = np.ctypeslib.as_array(out.xu_best, shape=(self.d["traj"],)).copy()
         return res

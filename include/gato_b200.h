@@ -108,6 +108,22 @@ int gato_mpc_step(gato_solver* s, const float* h_x_curr /*[nx]*/, const float* h
                   const float* h_u_last /*[nu] or NULL*/, float sim_dt, float timestep, int flags, gato_mpc_out* out, gato_stats* stats);
 int gato_mpc_get_warm_start(gato_solver* s, float* h_xu /*[B][traj]*/);
 
+/* The same step cut at the points where the ranks of a multi-GPU closed loop exchange data (the batch of hypotheses sharded over GPUs,
+ * BASELINE.json config 5; mpc_controller.py:233-253, 294-309).  All three calls only enqueue on the solver's stream; pointers are DEVICE pointers:
+ *   gato_mpc_local_async   d_in = [x_curr nx | ref window 6N | x_last nx | u_last nu] (e.g. just broadcast by NCCL); prepare, (reset_rho,) solve,
+ *                          score this shard's hypotheses (if score != 0); writes the shard's winner record to d_record:
+ *                          floats [0..1] error (one double) | [2] local id (int32) | [3] unused | [4 .. 4+traj) the winner's trajectory
+ *   gato_mpc_adopt_async   d_records = n_records records, record_stride floats apart, in shard order (e.g. just all-gathered by NCCL): the global
+ *                          winner by np.argmin semantics over the concatenated batch (first minimum, first NaN wins) becomes every local warm
+ *                          start; its global id is shard * id_stride + local id
+ *   gato_mpc_wait          synchronise and collect: out->best_id is the GLOBAL id, out->errors this shard's errors
+ * gato_mpc_step is local + adopt (one record) + wait. */
+int gato_mpc_record_floats(const gato_solver* s);
+int gato_mpc_input_floats(const gato_solver* s);
+int gato_mpc_local_async(gato_solver* s, const float* d_in, int score, float sim_dt, float timestep, int flags, float* d_record);
+int gato_mpc_adopt_async(gato_solver* s, const float* d_records, int n_records, int record_stride, int id_stride);
+int gato_mpc_wait(gato_solver* s, gato_mpc_out* out, gato_stats* stats);
+
 /* Introspection */
 int  gato_dims(int plant, int knot_points, int* nx, int* nu, int* traj_size);
 long gato_kernel_launches(const gato_solver* s); /* kernels launched by this solver so far */

@@ -22,7 +22,7 @@ def lib():
 
 def test_exports_every_declared_symbol(lib):
     hdr = (ROOT / "include" / "gato_b200.h").read_text()
-    names = sorted(set(re.findall(r"^\s*(?:int|void|long|const char\*)\s+(gato_[a-z_]+)\s*\(", hdr, flags=re.M)))
+    names = sorted(set(re.findall(r"^\s*(?:int|void|long|const char\*)\s+(gato_[a-z0-9_]+)\s*\(", hdr, flags=re.M)))
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), f"{n} declared in gato_b200.h but not exported"
