@@ -53,7 +53,14 @@ def stage_inputs(plant, N, B, cfg, seed):
     return w, xu, fext
 
 
-def gen_for_lib(plant, N, mode, cfg, out_dir, keep=2):
+def gen_for_lib(plant, N, mode, cfg, out_dir, keep=2, stages_only=False):
+    """stages_only: the dynamics dump and the per-stage chain only, no whole solves, with the merit stage launched through the harness's
+    GREF_MERIT_EXTRA_SMEM switch (the SAME unmodified kernel with enough dynamic shared memory).  This is how indy7 is pinned: its merit kernel
+    writes past the shared memory the reference's own launcher requests and faults on B200, so BSQP::solve cannot run."""
+    import os
+
+    if stages_only:
+        os.environ["GREF_MERIT_EXTRA_SMEM"] = "4096"
     be = Backend("ref", plant, N, mode)
     d = dims(plant, N)
     nq = d["nq"]
@@ -96,6 +103,11 @@ def gen_for_lib(plant, N, mode, cfg, out_dir, keep=2):
     # the line-search golden keeps ALL B rows but only compact outputs (+ the failure row)
     G.update(st_ls_merit8=m8, st_ls_merit_init=mi, st_ls_rho_in=rho, st_ls_step=ls["step"], st_ls_rho=ls["rho"], st_ls_drho=ls["drho"], st_ls_merit_out=ls["merit_init"],
              st_ls_xu_in=xu, st_ls_dz=dz, st_ls_xu_out=ls["xu"])
+    if stages_only:
+        G["stages_only"] = np.int32(1)
+        np.savez_compressed(out_dir / f"golden_{plant}_N{N}_{mode}.npz", **G)
+        print("wrote (stages only)", plant, N, mode, flush=True)
+        return
     # ---- whole solves --------------------------------------------------------------------------
     for Bs in be.batches:
         ws = make_config(cfg, B=Bs, N=N)
@@ -188,6 +200,7 @@ def main():
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "golden"))
     ap.add_argument("--timing", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--stages-only", action="store_true", help="with --only: dynamics + stage chain, merit through GREF_MERIT_EXTRA_SMEM (indy7)")
     a = ap.parse_args()
     out = Path(a.out)
     out.mkdir(parents=True, exist_ok=True)
@@ -206,7 +219,7 @@ def main():
             if a.only != name:
                 continue
             try:
-                gen_for_lib(plant, N, mode, cfg, out, keep=1 if N >= 128 else 2)
+                gen_for_lib(plant, N, mode, cfg, out, keep=1 if N >= 128 else 2, stages_only=a.stages_only)
             except FileNotFoundError as e:
                 print("skip (not built):", e, flush=True)
         else:

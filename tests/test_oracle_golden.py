@@ -38,8 +38,10 @@ def _stage_outputs(be, G):
     return out
 
 
-@pytest.mark.parametrize("plant,N", [("iiwa14", 8), ("iiwa14", 32)])
+@pytest.mark.parametrize("plant,N", [("iiwa14", 8), ("iiwa14", 32), ("indy7", 32)])
 def test_oracle_bit_exact_vs_reference_ieee_build(oracle_built, plant, N):
+    """indy7: the fixture holds the dynamics dump and the stage chain only (`oracle/gen_golden.py --stages-only`: the reference's indy7 merit
+    kernel faults on B200 through its own launcher, so the harness launches the same unmodified kernel with enough shared memory)."""
     G = load_golden(plant, N, "ieee")
     be = Backend("oracle", plant, N)
     dd = be.dyn_dump(G["dyn_x"], G["dyn_u"], G["dyn_fext"])
