@@ -3,7 +3,7 @@
 # they lie) into oracle/_ref/libgref_<plant>_N<N>_<fast|ieee>.so through oracle/ref_harness.cu.
 #   fast = the reference's own flags (CMakeLists.txt:20-22: -O3 -use_fast_math -DNDEBUG), arch swapped to sm_100
 #   ieee = same without -use_fast_math (isolates fast-math noise from algorithmic parity)
-# Usage: oracle/build_ref.sh                 the two libraries the GPU box uses: bench.py's (iiwa14 N=32, fast) and the live parity test's (ieee)
+# Usage: oracle/build_ref.sh                 the libraries the GPU box uses: bench.py's (iiwa14 N=32, fast) and the live parity tests' (iiwa14 / indy7 N=32, ieee)
 #        oracle/build_ref.sh all             every library oracle/gen_golden.py needs, in parallel
 #        oracle/build_ref.sh pin             the IEEE builds the tools/pin_*.py comparisons use
 #        oracle/build_ref.sh plant N batches mode [...]
@@ -51,9 +51,13 @@ if [ "${1:-}" != all ]; then
   p1=$!
   build_one iiwa14 32 16,128 ieee &
   p2=$!
+  # indy7: the live stage-chain parity test (tests/test_gpu_reference_live.py) and the stage fixture (gen_golden.py --stages-only)
+  build_one indy7 32 16 ieee &
+  p3=$!
   rc=0
   wait $p1 || rc=1
   wait $p2 || rc=1
+  wait $p3 || rc=1
   exit $rc
 fi
 JOBS=${GREF_JOBS:-6}
