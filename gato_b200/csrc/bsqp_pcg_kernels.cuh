@@ -59,15 +59,19 @@ constexpr int cp_bytes(int block_floats) { return (block_floats * 4) % 16 == 0 ?
 // stored back into q, r (computeDzBatchedKernel, schur_linsys.cuh:331-430).  One warp per knot; wbuf = 64 floats per warp.
 template<int NX, int NU, int LDV = NX>
 __device__ __forceinline__ void dz_phase(const Ctx& c, int b, int N, int n, int warp, int lane, int nwarps, float* dzbuf, const float* lam, const float* Ab, const float* Bb,
-                                         const float* Qib, const float* Rib, const float* qb, const float* rb)
+                                         const float* Qib, const float* Rib, const float* qb, const float* rb, int k_begin = 0, int k_end = -1)
 {
-        // lam: this solve's padded lambda; Ab, Bb, Qib, Rib, qb, rb: its A, B, Q^-1, R^-1, q, r blocks (knot k at k * block size) -- in global
-        // memory, or (k_pcg) prefetched to shared memory.  The residuals are written back to c.q / c.r in global memory either way.
+        // knots k_begin .. k_end-1 (default: all).  lam: padded lambda, block of knot k_begin - 1 first; Ab, Bb, Qib, Rib, qb, rb: the A, B, Q^-1,
+        // R^-1, q, r blocks of these knots (knot k at (k - k_begin) * block size) -- in global memory, or prefetched to shared memory.  The
+        // residuals are written back to c.q / c.r in global memory either way.
         constexpr int NX2 = NX * NX;
         const size_t  kb = (size_t)b * N;
         float*        wbuf = dzbuf + warp * 64;
         const int     traj = (NX + NU) * N - NU;
-        for (int k = warp; k < N; k += nwarps) {
+        if (k_end < 0) k_end = N;
+        lam -= (size_t)k_begin * LDV;
+        Ab -= (size_t)k_begin * NX2, Bb -= (size_t)k_begin * NX * NU, Qib -= (size_t)k_begin * NX2, Rib -= (size_t)k_begin * NU * NU, qb -= (size_t)k_begin * NX, rb -= (size_t)k_begin * NU;
+        for (int k = k_begin + warp; k < k_end; k += nwarps) {
                 const float* lk = lam + (k + 1) * LDV;  // LDV: floats between consecutive blocks of lambda (NX: packed; kSlot: k_pcg's slotted vectors)
                 const float* lk1 = lam + (k + 2) * LDV;
                 __syncwarp();
@@ -722,6 +726,302 @@ __global__ void __launch_bounds__(1024, 1) k_pcg_stream(Ctx c)
         if (c.flags & F_DZ)
                 dz_phase<NX, NU>(c, b, N, n, warp, lane, nwarps, dzbuf, c.lambda + (size_t)b * n, c.A + kb * NX2, c.Bm + kb * NX * NU, c.Qinv + kb * NX2, c.Rinv + kb * NU * NU, c.q + kb * NX,
                                  c.r + kb * NU);
+}
+
+
+// -----------------------------------------------------------------------------------------------------
+// k_pcg_cluster: the register-resident PCG for horizons that do not fit one CTA's register file (N = 35 ... 144 for iiwa14, e.g. BASELINE
+// config 4, N = 128): a THREAD-BLOCK CLUSTER of CL CTAs per solve.  CTA c keeps the rows of S and P^-1 of block rows [c*NB, (c+1)*NB) in
+// registers exactly like k_pcg (one row per thread, packed FFMA2 row trees), so the whole system (588 KB at N = 128) stays on chip for all
+// iterations -- k_pcg_stream re-reads it from L2 in every iteration, as the reference does from global memory (pcg.cuh:100,119).  What crosses
+// CTAs goes through DISTRIBUTED SHARED MEMORY (st.shared::cluster to mapa addresses) and four cluster barriers per iteration:
+//   * the window halos: one block of Ap (or z) to each neighbour ahead of the dot product's barrier; the neighbour then updates its copy of my
+//     boundary block of r (or p) itself with the same fused multiply-add, so the vector updates need no barrier of their own;
+//   * the dot products in the reference's block::dot geometry (linalg.cuh:291-327: 1024 virtual threads, virtual thread t accumulates elements
+//     t and t + 1024 in that order, warp tree, tree over the 32 warp sums): every thread posts its term -- fmaf(a, b, 0) of element t, or the
+//     operands (a, b) of element t + 1024 -- into the inbox of the CTA that reduces virtual warp t / 32 [barrier], the reducer warps finish
+//     fmaf(a', b', first), run the shuffle tree and post the warp sum into every CTA's table [barrier], and every thread folds the table.
+// The rows and the primal step's operands arrive through the TMA unit (cp.async.bulk + mbarrier).  P^-1 is read complete: its off-diagonal blocks
+// are built beforehand by k_pcg_stream's K2 phase (once per SQP iteration).
+// -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned cluster_rank()
+{
+        unsigned r;
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+        return r;
+}
+__device__ __forceinline__ unsigned mapa_cluster(unsigned laddr, unsigned rank)  // this CTA's shared address -> the same offset in CTA `rank` of the cluster
+{
+        unsigned r;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(laddr), "r"(rank));
+        return r;
+}
+__device__ __forceinline__ void st_cluster(unsigned raddr, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory"); }
+__device__ __forceinline__ void cluster_sync()
+{
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template<class P>
+struct ClusterGeom {
+        static constexpr int NX = 2 * P::NQ;
+        static constexpr int NB = (P::NQ == 7) ? 32 : 40;  // block rows per CTA: NB * NX is a multiple of 32 (448 = 14 warps, 480 = 15 warps)
+        static constexpr int T = NB * NX;
+        static_assert(T % 32 == 0 && T <= 512, "whole warps, one row per thread");
+        __host__ __device__ static constexpr int ctas(int N) { return (N + NB - 1) / NB; }
+        // virtual warps of the reference's 1024-thread dot product reduced by one CTA, and floats of its inbox (first terms | a | b)
+        __host__ __device__ static constexpr int vw_per_cta(int N) { return (32 + ctas(N) - 1) / ctas(N); }
+        __host__ __device__ static constexpr bool supported(int N) { return (N + 2) * NX > 512 && (N + 2) * NX <= 2048 && ctas(N) <= 8; }
+        __host__ __device__ static constexpr size_t smem_floats(int N)
+        {
+                const int stage = 3 * NB * NX * NX > dz_stage_floats<NX, P::NQ>(NB) ? 3 * NB * NX * NX : dz_stage_floats<NX, P::NQ>(NB);
+                return 4 + 2 * (size_t)(NB + 2) * kSlot + 4 * 16 + 3 * 32 * (size_t)vw_per_cta(N) + 32 + 64 * (size_t)(T / 32) + (size_t)stage;
+        }
+};
+
+template<class P>
+__global__ void __launch_bounds__(ClusterGeom<P>::T, 1) k_pcg_cluster(Ctx c)
+{
+        using G = ClusterGeom<P>;
+        constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ, NX2 = NX * NX, W = 3 * NX, NP = W / 2, NB = G::NB, T = G::T;
+        if (stopped_before(c, c.it)) return;  // uniform over the grid: whole clusters leave together
+        extern __shared__ __align__(16) float sm[];
+        const int      N = c.N, n = (N + 2) * NX, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+        const int      CL = G::ctas(N), VWPC = G::vw_per_cta(N);
+        const unsigned rank = cluster_rank();
+        const int      b = blockIdx.x / CL;
+        const int      kb0 = (int)rank * NB;                          // first block row (knot) of this CTA
+        const int      nbl = (N - kb0 < NB) ? (N - kb0) : NB;         // block rows it owns
+        const int      nrows = nbl * NX;
+        // shared memory: 2 mbarriers | vp, vr: NB+2 slots (slot j = padded block kb0 + j: own blocks in 1..NB, halos in 0 and NB+1) |
+        // halo inboxes (Ap / z from below and above) | dot inbox (first | a | b) | table of the 32 warp sums | dz scratch | stage
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm);
+        float*              vp = sm + 4;
+        float*              vr = vp + (NB + 2) * kSlot;
+        float*              halo_in = vr + (NB + 2) * kSlot;  // [0] Ap from below, [1] Ap from above, [2] z from below, [3] z from above (16 floats each)
+        float*              inbox = halo_in + 4 * 16;         // first[32 VWPC] | a[32 VWPC] | b[32 VWPC]
+        float*              sums = inbox + 3 * 32 * VWPC;
+        float*              dzbuf = sums + 32;
+        float*              stage = dzbuf + 64 * nwarps;
+        const size_t        kb = (size_t)b * N;
+        const float*        gS = c.S + (kb + kb0) * 3 * NX2;
+        const float*        gP = c.Pinv + (kb + kb0) * 3 * NX2;
+        const bool          row_ok = tid < nrows;
+        const int           brl = tid / NX;                       // local block row
+        const int           i_glob = NX + kb0 * NX + tid;         // padded vector index of this thread's element
+        const int           own = (brl + 1) * kSlot + tid % NX;   // its place in the slotted local vectors
+        const bool          has_lo = rank > 0, has_hi = (int)rank + 1 < CL;
+
+        if (tid == 0) {
+                mbar_init(&bars[0], 1);
+                mbar_init(&bars[1], 1);
+                fence_mbar_init();
+        }
+        for (int i = tid; i < 2 * (NB + 2) * kSlot + 4 * 16 + 3 * 32 * VWPC + 32; i += T) vp[i] = 0.0f;  // vectors, halo inboxes, dot inbox, sums
+        __syncthreads();
+        cluster_sync();  // every CTA's shared memory is initialised before anyone posts into it
+
+        float2 S2[NP], P2[NP];
+        sfor<0, NP>([&](auto ic) { S2[ic] = make_float2(0.0f, 0.0f), P2[ic] = make_float2(0.0f, 0.0f); });
+        if (c.flags & F_PCG) {
+                // this CTA's rows of S, then of P^-1, through the TMA unit into the stage and from there into registers
+                const unsigned bytes = sizeof(float) * (unsigned)nrows * W;
+                if (tid == 0 && nrows > 0) {
+                        mbar_arrive_expect_tx(&bars[0], bytes);
+                        bulk_g2s(stage, gS, bytes, &bars[0]);
+                }
+                if (nrows > 0) mbar_wait(&bars[0], 0);
+                if (row_ok) {
+                        const float2* s2 = reinterpret_cast<const float2*>(stage + (size_t)tid * W);
+                        sfor<0, NP>([&](auto ic) { S2[ic] = s2[ic]; });
+                }
+                fence_proxy_async();
+                __syncthreads();
+                if (tid == 0 && nrows > 0) {
+                        mbar_arrive_expect_tx(&bars[0], bytes);
+                        bulk_g2s(stage, gP, bytes, &bars[0]);
+                }
+                if (nrows > 0) mbar_wait(&bars[0], 1);
+                if (row_ok) {
+                        const float2* p2 = reinterpret_cast<const float2*>(stage + (size_t)tid * W);
+                        sfor<0, NP>([&](auto ic) { P2[ic] = p2[ic]; });
+                }
+        }
+        // the primal step's operands of this CTA's knots, prefetched into the stage while the iterations run (as in k_pcg)
+        float*     sA = stage;
+        float*     sB = sA + pad4(NB * NX2);
+        float*     sQi = sB + pad4(NB * NX * NU);
+        float*     sRi = sQi + pad4(NB * NX2);
+        float*     sq = sRi + pad4(NB * NU * NU);
+        float*     sr = sq + pad4(NB * NX);
+        const bool bulk_dz = dz_bulk_ok<NX, NU>(nbl) && dz_bulk_ok<NX, NU>(kb0) && dz_bulk_ok<NX, NU>(N) && nbl > 0;
+        if (c.flags & F_DZ) {
+                fence_proxy_async();
+                __syncthreads();
+                if (bulk_dz && tid == 0) {
+                        const unsigned bA = 4u * nbl * NX2, bB = 4u * nbl * NX * NU, bR = 4u * nbl * NU * NU, bq = 4u * nbl * NX, br_ = 4u * nbl * NU;
+                        mbar_arrive_expect_tx(&bars[1], 2 * bA + bB + bR + bq + br_);
+                        bulk_g2s(sA, c.A + (kb + kb0) * NX2, bA, &bars[1]);
+                        bulk_g2s(sB, c.Bm + (kb + kb0) * NX * NU, bB, &bars[1]);
+                        bulk_g2s(sQi, c.Qinv + (kb + kb0) * NX2, bA, &bars[1]);
+                        bulk_g2s(sRi, c.Rinv + (kb + kb0) * NU * NU, bR, &bars[1]);
+                        bulk_g2s(sq, c.q + (kb + kb0) * NX, bq, &bars[1]);
+                        bulk_g2s(sr, c.r + (kb + kb0) * NU, br_, &bars[1]);
+                }
+        } else {
+                __syncthreads();
+        }
+
+        const unsigned a_vp = smem_u32(vp), a_vr = smem_u32(vr), a_halo = smem_u32(halo_in), a_inbox = smem_u32(inbox), a_sums = smem_u32(sums);
+        float          x_i = 0.0f;
+        int            iters = 0;
+        if (c.flags & F_PCG) {
+                const float* gam = c.gamma + (size_t)b * n;
+                float*       lam = c.lambda + (size_t)b * n;
+                const float  eps = c.pcg_tol[b];
+                const float  abs_tol = 1e-6f;
+                const bool   skip = c.conv[b] != 0;  // pcg.cuh:29-32
+                const unsigned wp = a_vp + 4u * (brl * kSlot), wr = a_vr + 4u * (brl * kSlot);  // window: slots brl .. brl+2
+                const unsigned own_p = a_vp + 4u * own, own_r = a_vr + 4u * own;
+                // where this thread's dot-product term goes: virtual thread t = i mod 1024 of virtual warp t / 32, reduced by CTA (t / 32) / VWPC
+                const int      vt = i_glob & 1023, rc = (vt >> 5) / VWPC, q = vt - rc * VWPC * 32;
+                const bool     second = i_glob >= 1024;
+                const unsigned post_f = mapa_cluster(a_inbox + 4u * q, rc), post_a = mapa_cluster(a_inbox + 4u * (32 * VWPC + q), rc),
+                               post_b = mapa_cluster(a_inbox + 4u * (64 * VWPC + q), rc);
+                // the first NX threads post the first block to the CTA below, the next NX threads the last block to the CTA above
+                const bool     send_lo = has_lo && tid < NX, send_hi = has_hi && tid >= NX && tid < 2 * NX;
+                const int      hx = send_lo ? tid : tid - NX;  // element within the boundary block
+                // boundary values live in other threads' registers: they go through a small exchange row
+                float* xch = dzbuf;  // 2 x 16 floats: this CTA's first and last block of the freshly computed vector (Ap or z)
+                auto   post_halo = [&](int kind) {
+                        // kind 0: Ap, 1: z.  My first block is the "from above" halo of the CTA below; my last block the "from below" halo of the CTA above.
+                        if (send_lo) st_cluster(mapa_cluster(a_halo + 4u * ((2 * kind + 1) * 16 + hx), rank - 1), xch[hx]);
+                        if (send_hi) st_cluster(mapa_cluster(a_halo + 4u * ((2 * kind + 0) * 16 + hx), rank + 1), xch[16 + hx]);
+                };
+                auto   publish_boundary = [&](float v) {
+                        if (row_ok && brl == 0) xch[tid] = v;
+                        if (row_ok && brl == nbl - 1) xch[16 + tid - (nbl - 1) * NX] = v;
+                };
+                auto dot_post = [&](float a, float bb) {
+                        if (row_ok) {
+                                if (!second)
+                                        st_cluster(post_f, fmaf(a, bb, 0.0f));
+                                else
+                                        st_cluster(post_a, a), st_cluster(post_b, bb);
+                        }
+                };
+                // after the first barrier: the reducer warps finish the virtual threads, run the warp tree and post the sums to every CTA
+                auto dot_reduce = [&]() {
+                        for (int vw = warp; vw < VWPC; vw += nwarps) {
+                                const int   gvw = (int)rank * VWPC + vw;
+                                const float f = inbox[32 * vw + lane], a = inbox[32 * VWPC + 32 * vw + lane], bb = inbox[64 * VWPC + 32 * vw + lane];
+                                const float sum = __shfl_sync(0xffffffffu, warp_tree(fmaf(a, bb, f)), 0);
+                                if (gvw < 32 && lane < CL) st_cluster(mapa_cluster(a_sums + 4u * gvw, lane), sum);  // lane l posts to CTA l
+                        }
+                };
+                if (!skip) {
+                        x_i = row_ok ? lam[i_glob] : 0.0f;
+                        if (row_ok) sts32(own_p, x_i);  // vp temporarily holds x for r = gamma - S x; its halos come straight from global memory
+                        if (tid < NX) {
+                                vp[tid] = lam[kb0 * NX + tid];  // padded block kb0 (the block below; zeros for the first CTA)
+                                vp[(nbl + 1) * kSlot + tid] = lam[(kb0 + nbl + 1) * NX + tid];
+                        }
+                        __syncthreads();
+                        float r_i = 0.0f, p_i = 0.0f, z_i = 0.0f;
+                        {
+                                const float sx = row_ok ? matvec_packed<NX>(S2, wp) : 0.0f;
+                                r_i = row_ok ? (gam[i_glob] - sx) : 0.0f;
+                                if (row_ok) sts32(own_r, r_i);
+                                __syncthreads();
+                                // r halos: posted straight into the neighbours' vr halo slots
+                                if (send_lo) st_cluster(mapa_cluster(a_vr + 4u * ((NB + 1) * kSlot + hx), rank - 1) , vr[kSlot + hx]);
+                                if (send_hi) st_cluster(mapa_cluster(a_vr + 4u * hx, rank + 1), vr[nbl * kSlot + hx]);
+                        }
+                        cluster_sync();
+                        // (only the last CTA can be partial, and it has no neighbour above: a CTA that receives an upper halo is full, slot NB+1)
+                        z_i = row_ok ? matvec_packed<NX>(P2, wr) : 0.0f;
+                        p_i = z_i;
+                        __syncthreads();  // every row is done reading vp as x
+                        if (row_ok) sts32(own_p, p_i);
+                        publish_boundary(z_i);
+                        dot_post(r_i, z_i);
+                        __syncthreads();
+                        // p halos (= z): straight into the neighbours' vp halo slots
+                        if (send_lo) st_cluster(mapa_cluster(a_vp + 4u * ((NB + 1) * kSlot + hx), rank - 1), xch[hx]);
+                        if (send_hi) st_cluster(mapa_cluster(a_vp + 4u * hx, rank + 1), xch[16 + hx]);
+                        cluster_sync();
+                        dot_reduce();
+                        cluster_sync();
+                        float rho = tree32(a_sums);
+                        if (!(fabsf(rho) < abs_tol)) {
+                                const float rho_init = fabsf(rho);
+                                for (int itn = 0; itn < c.max_pcg; itn++) {
+                                        iters++;
+                                        const float Ap_i = row_ok ? matvec_packed<NX>(S2, wp) : 0.0f;
+                                        publish_boundary(Ap_i);
+                                        dot_post(p_i, Ap_i);
+                                        __syncthreads();
+                                        post_halo(0);
+                                        cluster_sync();
+                                        dot_reduce();
+                                        cluster_sync();
+                                        const float alpha = rho / tree32(a_sums);
+                                        x_i = fmaf(alpha, p_i, x_i);
+                                        r_i = fmaf(-alpha, Ap_i, r_i);
+                                        if (row_ok) sts32(own_r, r_i);
+                                        // my copies of the neighbours' boundary blocks of r, updated with the same fused multiply-add they use
+                                        if (has_lo && tid < NX) vr[tid] = fmaf(-alpha, halo_in[0 * 16 + tid], vr[tid]);
+                                        if (has_hi && tid >= NX && tid < 2 * NX) vr[(NB + 1) * kSlot + tid - NX] = fmaf(-alpha, halo_in[1 * 16 + tid - NX], vr[(NB + 1) * kSlot + tid - NX]);
+                                        __syncthreads();
+                                        z_i = row_ok ? matvec_packed<NX>(P2, wr) : 0.0f;
+                                        publish_boundary(z_i);
+                                        dot_post(r_i, z_i);
+                                        __syncthreads();
+                                        post_halo(1);
+                                        cluster_sync();
+                                        dot_reduce();
+                                        cluster_sync();
+                                        const float rho_new = tree32(a_sums);
+                                        if (fabsf(rho_new) < fmaf(eps, rho_init, abs_tol)) break;
+                                        const float beta = rho_new / rho;
+                                        rho = rho_new;
+                                        p_i = fmaf(beta, p_i, z_i);
+                                        if (row_ok) sts32(own_p, p_i);
+                                        if (has_lo && tid < NX) vp[tid] = fmaf(beta, vp[tid], halo_in[2 * 16 + tid]);
+                                        if (has_hi && tid >= NX && tid < 2 * NX) vp[(NB + 1) * kSlot + tid - NX] = fmaf(beta, vp[(NB + 1) * kSlot + tid - NX], halo_in[3 * 16 + tid - NX]);
+                                        __syncthreads();
+                                }
+                                if (row_ok) lam[i_glob] = x_i;
+                        }
+                }
+                if (tid == 0 && rank == 0) {
+                        if (c.pcg_log) c.pcg_log[(size_t)c.it * c.B + b] = iters;
+                        if (c.flags & F_BOOK) {
+                                int cv = c.conv[b];
+                                if (iters == 0) cv = 1;
+                                c.conv[b] = cv;
+                                if (cv) atomicAdd(&c.num_solved[c.it], 1u);
+                        }
+                }
+        }
+        // lambda of the neighbouring block above is needed by the primal step: make this CTA's lambda visible, then everybody reads global memory
+        __threadfence();
+        cluster_sync();
+        if (c.flags & F_DZ) {
+                const float* lamg = c.lambda + (size_t)b * n;
+                for (int i = tid; i < (nbl + 2) * NX; i += T) vp[(i / NX) * kSlot + i % NX] = lamg[kb0 * NX + i];  // padded blocks kb0 .. kb0+nbl+1
+                if (bulk_dz) mbar_wait(&bars[1], 0);
+                __syncthreads();
+                if (nbl > 0) {
+                        if (bulk_dz)
+                                dz_phase<NX, NU, kSlot>(c, b, N, n, warp, lane, nwarps, dzbuf, vp, sA, sB, sQi, sRi, sq, sr, kb0, kb0 + nbl);
+                        else
+                                dz_phase<NX, NU, kSlot>(c, b, N, n, warp, lane, nwarps, dzbuf, vp, c.A + (kb + kb0) * NX2, c.Bm + (kb + kb0) * NX * NU, c.Qinv + (kb + kb0) * NX2,
+                                                        c.Rinv + (kb + kb0) * NU * NU, c.q + (kb + kb0) * NX, c.r + (kb + kb0) * NU, kb0, kb0 + nbl);
+                }
+        }
+        cluster_sync();  // nobody leaves while a neighbour may still post into its shared memory
 }
 
 }  // namespace gato

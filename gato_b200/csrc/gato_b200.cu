@@ -111,6 +111,7 @@ struct gato_solver {
         bool                                           pending = false;
         size_t                                         smem_pcg = 0, smem_schur = 0;
         int                                            pcg_threads = 0, pcg_rpt = 0;
+        bool                                           pcg_cluster = false;  // long horizons: thread-block cluster per solve (k_pcg_cluster) instead of streaming
 
         gato_solver(int plant_, int N_, int B_, int dev) : plant(plant_), N(N_), B(B_), device(dev), d(plant_ ? 7 : 6, N_), prm{}, max_it(1), n_it(1) {}
 };
@@ -140,6 +141,8 @@ int configure_kernels(gato_solver* s)
                         return GATO_ERR_UNSUPPORTED;
                 }
                 s->pcg_threads = 1024;
+                // GATO_PCG_NO_CLUSTER=1 keeps the streaming kernel (A/B measurements)
+                s->pcg_cluster = pcg_cluster_supported<P>(s->N) && !getenv("GATO_PCG_NO_CLUSTER");
                 // vectors | dot scratch | dz scratch | max(K2 scratch, 32 per-warp tiles of 32 rows x 3nx floats)
                 s->smem_pcg = sizeof(float) * ((size_t)2 * n + 64 + 64 * 32 + std::max((size_t)(s->N - 1) * 4 * P::NQ * P::NQ, (size_t)32 * 32 * 6 * P::NQ));
         } else {
@@ -204,8 +207,7 @@ template<class P>
 void launch_pcg(gato_solver* s, const Ctx& c)
 {
         tick(s, 2);
-        enqueue_pcg<P>(c, s->pcg_rpt, s->pcg_threads, s->smem_pcg, s->stream);
-        s->launches++;
+        s->launches += enqueue_pcg<P>(c, s->pcg_rpt, s->pcg_threads, s->smem_pcg, s->pcg_cluster, s->stream);
 }
 template<class P, int NA>
 void launch_merit(gato_solver* s, const Ctx& c)

@@ -19,9 +19,13 @@ template<class P>
 void enqueue_kkt(const Ctx& c, cudaStream_t st);
 template<class P>
 void enqueue_schur(const Ctx& c, size_t smem, cudaStream_t st);
-// rpt = 0: register-resident k_pcg with `threads` threads; rpt = 1..4: k_pcg_stream<rpt> with 1024 threads
+// rpt = 0: register-resident k_pcg with `threads` threads; rpt = 1..4: k_pcg_stream<rpt> with 1024 threads, or -- cluster = true -- the
+// cluster kernel k_pcg_cluster (after k_pcg_stream's K2 phase when F_K2 is set).  Returns the number of kernels launched.
 template<class P>
-void enqueue_pcg(const Ctx& c, int rpt, int threads, size_t smem, cudaStream_t st);
+int enqueue_pcg(const Ctx& c, int rpt, int threads, size_t smem, bool cluster, cudaStream_t st);
+// horizons the cluster kernel serves: too long for one CTA's registers, at most 2048 padded vector entries and 8 CTAs per solve
+template<class P>
+bool pcg_cluster_supported(int N);
 // opt in to the device's maximum dynamic shared memory for every linear-algebra kernel (the attribute is global per kernel and device)
 template<class P>
 cudaError_t configure_linalg(int device);

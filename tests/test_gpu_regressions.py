@@ -137,3 +137,26 @@ def test_kkt_residual_log(backends):
     _, qres, _ = o.stage_dz(B, lam, sc["Qinv"], sc["Rinv"], kk["q"], kk["r"], kk["A"], kk["Bm"])
     assert n_mismatch(qm[0], np.abs(qres.reshape(B, -1)).max(1)) == 0
     assert n_mismatch(cm[0], np.abs(kk["c"].reshape(B, -1)).max(1)) == 0
+
+
+@pytest.mark.parametrize("plant,N", [("iiwa14", 35), ("iiwa14", 64), ("iiwa14", 65), ("iiwa14", 97), ("iiwa14", 128), ("iiwa14", 144), ("indy7", 41), ("indy7", 80), ("indy7", 121), ("indy7", 168)])
+def test_cluster_pcg_kernel_long_horizons(backends, plant, N, monkeypatch):
+    """k_pcg_cluster (thread-block cluster per solve, rows in registers across 2 ... 5 CTAs, halos and dot products over distributed shared
+    memory): whole solves and the PCG stage bit-for-bit against the oracle, full and partial last CTAs, one and two elements per virtual
+    thread of the reference's 1024-thread dot product; and identical to the streaming kernel it replaces (GATO_PCG_NO_CLUSTER=1)."""
+    o, g = backends(plant, N)
+    B = 3
+    w = make_config(2 if plant == "iiwa14" else 3, B=B, N=N)
+    p = dict(w["params"], max_sqp_iters=2, max_pcg_iters=60, pcg_tol=1e-5)
+    ro, rg = o.solver(B, p).solve(w["xu"], w["xs"], w["ref"], w["dt"]), g.solver(B, p).solve(w["xu"], w["xs"], w["ref"], w["dt"])
+    assert np.array_equal(rg["pcg_iters"], ro["pcg_iters"]) and np.array_equal(rg["ls_step_size"], ro["ls_step_size"])
+    for k in ("XU", "final_merit"):
+        assert n_mismatch(rg[k], ro[k]) == 0, k
+    monkeypatch.setenv("GATO_PCG_NO_CLUSTER", "1")
+    rs = g.solver(B, p).solve(w["xu"], w["xs"], w["ref"], w["dt"])
+    monkeypatch.delenv("GATO_PCG_NO_CLUSTER")
+    assert n_mismatch(rs["XU"], rg["XU"]) == 0 and np.array_equal(rs["pcg_iters"], rg["pcg_iters"])
+    # fixed cap (no early exit) and a flagged solve
+    p2 = dict(p, max_sqp_iters=1, max_pcg_iters=25, pcg_tol=-1.0)
+    ro, rg = o.solver(B, p2).solve(w["xu"], w["xs"], w["ref"], w["dt"]), g.solver(B, p2).solve(w["xu"], w["xs"], w["ref"], w["dt"])
+    assert (rg["pcg_iters"] == 25).all() and n_mismatch(rg["XU"], ro["XU"]) == 0
