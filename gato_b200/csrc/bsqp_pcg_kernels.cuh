@@ -983,6 +983,9 @@ __global__ void __launch_bounds__(ClusterGeom<P>::T, 1) k_pcg_cluster(Ctx c)
                                         dot_reduce();
                                         cluster_sync();
                                         const float rho_new = tree32(a_sums);
+#ifdef GATO_CLUSTER_EXTRA_SYNC
+                                        for (int e_ = 0; e_ < GATO_CLUSTER_EXTRA_SYNC; e_++) cluster_sync();  // measurement only: the cost of one cluster barrier
+#endif
                                         if (fabsf(rho_new) < fmaf(eps, rho_init, abs_tol)) break;
                                         const float beta = rho_new / rho;
                                         rho = rho_new;
