@@ -15,9 +15,17 @@ template<class P, int NA, bool SPLIT = false>
 __global__ void __launch_bounds__(SPLIT ? 512 : (NA == 1 ? 128 : 256), (NA == 1 || SPLIT) ? 1 : GATO_MERIT_MIN_BLOCKS) k_merit_ls(Ctx c)
 {
         constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ;
-        if (NA > 1 && stopped_before(c, c.it + 1)) return;  // the iteration that meets the test skips merit + line search (bsqp.cuh:165)
-        extern __shared__ float smf[];                       // [NA][N] per-knot merits, NA sums, (SPLIT: [NA][N] cost halves)
+        const bool overlap = NA > 1 && (c.flags & F_OVERLAP) != 0;
+        // the iteration that meets the early-exit test skips merit + line search (bsqp.cuh:165).  Launched after the PCG launch has completed the
+        // test is final; overlapped with it (F_OVERLAP) only the earlier iterations are, and this iteration's test is decided before the line search
+        if (NA > 1 && stopped_before(c, overlap ? c.it : c.it + 1)) return;
+        extern __shared__ float smf[];  // [NA][N] per-knot merits, NA sums, (SPLIT: [NA][N] cost halves)
         const int               N = c.N, b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+        if (overlap) {
+                // this solve's primal step comes from a PCG CTA that may still be running: wait for its hand-over flag
+                if (tid == 0) wait_flag(c.pcg_done + (size_t)c.it * c.B + b);
+                __syncthreads();
+        }
         const int               traj = (NX + NU) * N - NU;
         float*                  mk = smf;
         float*                  msum = smf + NA * N;
@@ -90,6 +98,13 @@ __global__ void __launch_bounds__(SPLIT ? 512 : (NA == 1 ? 128 : 256), (NA == 1 
                 if (!(c.flags & F_LS)) return;
                 __shared__ float s_step;
                 __shared__ int   s_ok;
+                if (overlap) {
+                        // the merits above were computed speculatively; the line search only runs if this iteration does not meet the exit test
+                        __shared__ int s_stop;
+                        if (tid == 0) s_stop = stop_decided_early(c, c.it) ? 1 : 0;
+                        __syncthreads();
+                        if (s_stop) return;
+                }
                 if (tid == 0) {
                         // first strict minimum over the 8 merits; NaN / >= 1e38 count as 1e38 at index 0 (line_search.cuh:23-55)
                         float best = 1e38f;

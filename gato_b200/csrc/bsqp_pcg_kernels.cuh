@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pcg(Ctx c)
         // Thread t owns PADDED vector index i = t (so real warp w == virtual warp w of the reference's block::dot) and, for
         // NX <= i < NX + N*NX, matrix row r = i - NX: its rows of S and P^-1 and its elements of x, r, p live in registers, as float2 pairs.
         constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ, NX2 = NX * NX, W = 3 * NX, NP = W / 2, HP = NX / 2;
+        pdl_launch_dependents();  // the merit / line-search launch of this iteration may fill SMs this grid leaves idle (its last, partial wave)
         if (stopped_before(c, c.it)) return;
         extern __shared__ __align__(16) float sm[];
         const int                             N = c.N, b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
@@ -504,7 +505,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pcg(Ctx c)
                                 int cv = c.conv[b];
                                 if (iters == 0) cv = 1;
                                 c.conv[b] = cv;
-                                if (cv) atomicAdd(&c.num_solved[c.it], 1u);
+                                atomicAdd(cv ? &c.num_solved[c.it] : &c.num_unsolved[c.it], 1u);
                         }
                 }
                 __syncthreads();
@@ -519,6 +520,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_pcg(Ctx c)
                         asm volatile("cp.async.wait_all;" ::: "memory");
                 __syncthreads();
                 dz_phase<NX, NU, kSlot>(c, b, N, n, warp, lane, nwarps, dzbuf, vp, sA, sB, sQi, sRi, sq, sr);
+        }
+        if (c.flags & F_BOOK) {
+                // hand solve b over to a merit / line-search CTA that may already be waiting for it: every write of this CTA, then the flag
+                __syncthreads();
+                if (tid == 0) {
+                        __threadfence();
+                        st_release_gpu(c.pcg_done + (size_t)c.it * c.B + b, 1u);
+                }
         }
 }
 
@@ -718,7 +727,7 @@ __global__ void __launch_bounds__(1024, 1) k_pcg_stream(Ctx c)
                                 int cv = c.conv[b];
                                 if (iters == 0) cv = 1;
                                 c.conv[b] = cv;
-                                if (cv) atomicAdd(&c.num_solved[c.it], 1u);
+                                atomicAdd(cv ? &c.num_solved[c.it] : &c.num_unsolved[c.it], 1u);
                         }
                 }
                 __syncthreads();
@@ -1004,7 +1013,7 @@ __global__ void __launch_bounds__(ClusterGeom<P>::T, 1) k_pcg_cluster(Ctx c)
                                 int cv = c.conv[b];
                                 if (iters == 0) cv = 1;
                                 c.conv[b] = cv;
-                                if (cv) atomicAdd(&c.num_solved[c.it], 1u);
+                                atomicAdd(cv ? &c.num_solved[c.it] : &c.num_unsolved[c.it], 1u);
                         }
                 }
         }

@@ -98,7 +98,8 @@ struct gato_solver {
         float *          h_kkt_qmax = nullptr, *h_kkt_cmax = nullptr;
         bool             kkt_log = false;
         DevArr<float>    ee_q, ee_out;  // staging of gato_ee_pos
-        DevArr<unsigned> num_solved;
+        DevArr<unsigned> num_solved, num_unsolved, pcg_done;
+        bool             overlap = true;  // merit / line search overlapped with the tail of k_pcg (GATO_NO_OVERLAP=1 switches it off)
         DevArr<float>    st_xu, st_xs, st_ref, st_xkp1, st_xk, st_uk;  // staging for *_host calls
         // reset defaults of rho / drho (bsqp.cuh:48-58, 84-87, 189), resident on the device so that resets are device-to-device copies
         DevArr<float> rho_init, drho_init;
@@ -172,6 +173,7 @@ Ctx make_ctx(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref,
         c.rho = s->rho.p, c.drho = s->drho.p, c.merit = s->merit.p, c.merit_cur = s->merit_cur.p, c.step = s->step.p;
         c.mu = s->mu.p, c.pcg_tol = s->pcg_tol.p;
         c.kkt_qmax = s->kkt_log ? s->kkt_qmax.p : nullptr, c.kkt_cmax = s->kkt_log ? s->kkt_cmax.p : nullptr;
+        c.num_unsolved = s->num_unsolved.p, c.pcg_done = s->pcg_done.p;
         c.conv = s->conv.p, c.num_solved = s->num_solved.p, c.pcg_log = s->pcg_log.p, c.ls_merit_log = s->ls_merit_log.p, c.ls_step_log = s->ls_step_log.p;
         return c;
 }
@@ -226,6 +228,8 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
         s->n_ticks = 0;
         CUDA_TRY(s, cudaMemsetAsync(s->conv.p, 0, sizeof(int) * B, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->num_solved.p, 0, sizeof(unsigned) * s->max_it, s->stream));
+        CUDA_TRY(s, cudaMemsetAsync(s->num_unsolved.p, 0, sizeof(unsigned) * s->max_it, s->stream));
+        CUDA_TRY(s, cudaMemsetAsync(s->pcg_done.p, 0, sizeof(unsigned) * (size_t)s->max_it * B, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->pcg_log.p, 0, sizeof(int) * (size_t)s->max_it * B, s->stream));
         if (s->kkt_log) {
                 CUDA_TRY(s, cudaMemsetAsync(s->kkt_qmax.p, 0, sizeof(unsigned) * (size_t)s->max_it * B, s->stream));
@@ -253,13 +257,18 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
                 c.flags = F_CHECK_STOP;
                 launch_kkt<P>(s, c);
                 launch_schur<P>(s, c);
-                c.flags = F_CHECK_STOP | F_K2 | F_PCG | F_DZ | F_BOOK;
-                launch_pcg<P>(s, c);
                 if (!joined) {
+                        // the initial merit (side stream, beside k_kkt and k_schur) is joined ahead of the PCG launch: nothing may sit between
+                        // k_pcg and the line-search launch that overlaps its tail
                         CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
                         joined = true;
                 }
-                c.flags = F_CHECK_STOP | F_MERIT | F_LS;
+                c.flags = F_CHECK_STOP | F_K2 | F_PCG | F_DZ | F_BOOK;
+                launch_pcg<P>(s, c);
+                // the register-resident k_pcg hands solves over one by one: the line search may start under its last wave (not with per-kernel timing,
+                // whose events serialise the launches)
+                const bool ov = s->overlap && !s->timing && s->pcg_rpt == 0;
+                c.flags = F_CHECK_STOP | F_MERIT | F_LS | (ov ? F_OVERLAP : 0);
                 launch_merit<P, kNumAlphas>(s, c);
         }
         // Final merit on the updated trajectory (bsqp.cuh:180-182): no launch needed.  merit_cur[b] already holds it bit-for-bit: it is the
@@ -431,7 +440,7 @@ int gato_create(gato_solver** out, int plant, int N, int B, int device, void* st
         A(s->c, b * d.nx * N), A(s->Qinv, b * d.nx * d.nx * N), A(s->Rinv, b * d.nu * d.nu * N);
         A(s->S, b * d.brow * N), A(s->Pinv, b * d.brow * N), A(s->Pmain, b * d.nx * d.nx * N), A(s->gamma, b * d.vecp), A(s->lambda, b * d.vecp), A(s->dz, b * d.traj);
         A(s->rho, b), A(s->drho, b), A(s->rho_init, b), A(s->drho_init, b), A(s->mu, b), A(s->pcg_tol, b), A(s->fext, 6 * b), A(s->merit, kNumAlphas * b), A(s->merit_cur, b), A(s->merit0, b), A(s->step, b);
-        A(s->ls_merit_log, it * b), A(s->ls_step_log, it * b), A(s->conv, b), A(s->pcg_log, it * b), A(s->num_solved, it);
+        A(s->ls_merit_log, it * b), A(s->ls_step_log, it * b), A(s->conv, b), A(s->pcg_log, it * b), A(s->num_solved, it), A(s->num_unsolved, it), A(s->pcg_done, it * b);
         A(s->st_xu, b * d.traj), A(s->st_xs, b * d.nx), A(s->st_ref, b * 6 * N), A(s->st_xkp1, b * d.nx), A(s->st_xk, d.nx), A(s->st_uk, d.nu);
         if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_pcg_log, sizeof(int) * it * b);
         if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_conv, sizeof(int) * b);
@@ -450,6 +459,7 @@ int gato_create(gato_solver** out, int plant, int N, int B, int device, void* st
                 return fail(GATO_ERR_CUDA);
         }
         s->h_sqp_iters.assign(B, 0);
+        s->overlap = !getenv("GATO_NO_OVERLAP");
         // per-batch hyper-parameters  (bsqp.cuh:48-58)
         std::vector<float> rho0(B, prm->rho), drho0(B, 1.0f), mu(B, prm->mu), tol(B, prm->pcg_tol);
         cudaMemcpy(s->rho.p, rho0.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
@@ -474,7 +484,7 @@ void gato_destroy(gato_solver* s)
         for (auto* a : {&s->Q, &s->R, &s->q, &s->r, &s->A, &s->Bm, &s->c, &s->Qinv, &s->Rinv, &s->S, &s->Pinv, &s->Pmain, &s->gamma, &s->lambda, &s->dz, &s->rho, &s->drho, &s->rho_init, &s->drho_init, &s->mu, &s->pcg_tol, &s->fext,
                         &s->merit, &s->merit_cur, &s->merit0, &s->step, &s->ls_merit_log, &s->ls_step_log, &s->st_xu, &s->st_xs, &s->st_ref, &s->st_xkp1, &s->st_xk, &s->st_uk})
                 a->release();
-        s->conv.release(), s->pcg_log.release(), s->num_solved.release(), s->kkt_qmax.release(), s->kkt_cmax.release(), s->ee_q.release(), s->ee_out.release();
+        s->conv.release(), s->pcg_log.release(), s->num_solved.release(), s->num_unsolved.release(), s->pcg_done.release(), s->kkt_qmax.release(), s->kkt_cmax.release(), s->ee_q.release(), s->ee_out.release();
         if (s->h_kkt_qmax) cudaFreeHost(s->h_kkt_qmax);
         if (s->h_kkt_cmax) cudaFreeHost(s->h_kkt_cmax);
         for (void* p : {(void*)s->h_pcg_log, (void*)s->h_conv, (void*)s->h_num_solved, (void*)s->h_ls_merit, (void*)s->h_ls_step, (void*)s->h_final, (void*)s->h_initial})

@@ -31,9 +31,11 @@ template<class P>
 cudaError_t configure_linalg(int device);
 template<class P>
 size_t schur_smem_bytes();
-// num_alphas = 1 (initial / final merit) or kNumAlphas (merit + line search)
+// num_alphas = 1 (initial / final merit) or kNumAlphas (merit + line search).  c.flags & F_OVERLAP: launched with programmatic stream
+// serialization so that its CTAs may start while the preceding k_pcg launch drains (they wait per solve on the hand-over flags).
+// Returns false if the launch did not use the overlapped form (small batches use the split kernel).
 template<class P>
-void enqueue_merit(const Ctx& c, int num_alphas, cudaStream_t st);
+bool enqueue_merit(const Ctx& c, int num_alphas, cudaStream_t st);
 // end-effector position (forward kinematics) of n joint configurations: q[n][nq] -> ee[n][3]
 template<class P>
 void enqueue_ee_pos(int n, const float* q, float* ee, cudaStream_t st);

@@ -12,19 +12,35 @@ inline int merit_threads(int na, int N)
 }
 }  // namespace
 template<>
-void enqueue_merit<GATO_TU_PLANT>(const Ctx& c, int na, cudaStream_t st)
+bool enqueue_merit<GATO_TU_PLANT>(const Ctx& c, int na, cudaStream_t st)
 {
         const size_t smem = sizeof(float) * (size_t)(na * c.N + na);
         // small batches (one CTA per SM at most) with room for two threads per (alpha, knot) in one block: the split kernel
         if (na == kNumAlphas && c.B <= 148 && 2 * na * c.N <= 512) {
                 const int threads = (2 * na * c.N + 31) / 32 * 32;
-                k_merit_ls<GATO_TU_PLANT, kNumAlphas, true><<<c.B, threads, smem + sizeof(float) * (size_t)(na * c.N), st>>>(c);
-                return;
+                Ctx       k = c;
+                k.flags &= ~F_OVERLAP;
+                k_merit_ls<GATO_TU_PLANT, kNumAlphas, true><<<c.B, threads, smem + sizeof(float) * (size_t)(na * c.N), st>>>(k);
+                return false;
         }
-        if (na == 1)
+        if (na == 1) {
                 k_merit_ls<GATO_TU_PLANT, 1><<<c.B, merit_threads(1, c.N), smem, st>>>(c);
-        else
-                k_merit_ls<GATO_TU_PLANT, kNumAlphas><<<c.B, merit_threads(kNumAlphas, c.N), smem, st>>>(c);
+                return false;
+        }
+        if (c.flags & F_OVERLAP) {
+                // programmatic dependent launch: the grid may start once every CTA of the preceding k_pcg grid has started (k_pcg triggers at its
+                // top), i.e. during k_pcg's last, partial wave; per-solve ordering comes from the hand-over flags
+                cudaLaunchConfig_t  cfg{};
+                cudaLaunchAttribute at[1];
+                cfg.gridDim = dim3((unsigned)c.B), cfg.blockDim = dim3((unsigned)merit_threads(kNumAlphas, c.N)), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at, cfg.numAttrs = 1;
+                cudaLaunchKernelEx(&cfg, k_merit_ls<GATO_TU_PLANT, kNumAlphas, false>, c);
+                return true;
+        }
+        k_merit_ls<GATO_TU_PLANT, kNumAlphas><<<c.B, merit_threads(kNumAlphas, c.N), smem, st>>>(c);
+        return false;
 }
 template<>
 void enqueue_ee_pos<GATO_TU_PLANT>(int n, const float* q, float* ee, cudaStream_t st)
