@@ -766,6 +766,12 @@ __device__ __forceinline__ unsigned mapa_cluster(unsigned laddr, unsigned rank) 
         return r;
 }
 __device__ __forceinline__ void st_cluster(unsigned raddr, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory"); }
+// asynchronous store into another CTA's shared memory that completes 4 bytes of a transaction on THAT CTA's mbarrier: the receiver waits on its own
+// barrier phase instead of a cluster-wide barrier (st.async ... mbarrier::complete_tx::bytes)
+__device__ __forceinline__ void st_async_cluster(unsigned raddr, float v, unsigned rmbar)
+{
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(raddr), "f"(v), "r"(rmbar) : "memory");
+}
 __device__ __forceinline__ void cluster_sync()
 {
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -785,7 +791,7 @@ struct ClusterGeom {
         __host__ __device__ static constexpr size_t smem_floats(int N)
         {
                 const int stage = 3 * NB * NX * NX > dz_stage_floats<NX, P::NQ>(NB) ? 3 * NB * NX * NX : dz_stage_floats<NX, P::NQ>(NB);
-                return 4 + 2 * (size_t)(NB + 2) * kSlot + 4 * 16 + 3 * 32 * (size_t)vw_per_cta(N) + 32 + 64 * (size_t)(T / 32) + (size_t)stage;
+                return 8 + 2 * (size_t)(NB + 2) * kSlot + 4 * 16 + 3 * 32 * (size_t)vw_per_cta(N) + 32 + 64 * (size_t)(T / 32) + (size_t)stage;
         }
 };
 
@@ -803,10 +809,10 @@ __global__ void __launch_bounds__(ClusterGeom<P>::T, 1) k_pcg_cluster(Ctx c)
         const int      kb0 = (int)rank * NB;                          // first block row (knot) of this CTA
         const int      nbl = (N - kb0 < NB) ? (N - kb0) : NB;         // block rows it owns
         const int      nrows = nbl * NX;
-        // shared memory: 2 mbarriers | vp, vr: NB+2 slots (slot j = padded block kb0 + j: own blocks in 1..NB, halos in 0 and NB+1) |
+        // shared memory: 4 mbarriers (rows staged, dz operands staged, dot / halo inbox complete, warp-sum table complete) | vp, vr: NB+2 slots (slot j = padded block kb0 + j: own blocks in 1..NB, halos in 0 and NB+1) |
         // halo inboxes (Ap / z from below and above) | dot inbox (first | a | b) | table of the 32 warp sums | dz scratch | stage
         unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm);
-        float*              vp = sm + 4;
+        float*              vp = sm + 8;
         float*              vr = vp + (NB + 2) * kSlot;
         float*              halo_in = vr + (NB + 2) * kSlot;  // [0] Ap from below, [1] Ap from above, [2] z from below, [3] z from above (16 floats each)
         float*              inbox = halo_in + 4 * 16;         // first[32 VWPC] | a[32 VWPC] | b[32 VWPC]
@@ -822,10 +828,22 @@ __global__ void __launch_bounds__(ClusterGeom<P>::T, 1) k_pcg_cluster(Ctx c)
         const int           own = (brl + 1) * kSlot + tid % NX;   // its place in the slotted local vectors
         const bool          has_lo = rank > 0, has_hi = (int)rank + 1 < CL;
 
+        // bytes that arrive in this CTA's inbox per dot product: one float per first element and two per second element of the virtual threads it
+        // reduces (only real rows post), plus one boundary block from each neighbour; and 32 warp sums in its table
+        unsigned in_bytes;
+        {
+                const int lo = (int)rank * VWPC * 32, hi = (lo + VWPC * 32 < 1024) ? lo + VWPC * 32 : 1024, r0 = NX, r1 = NX + N * NX;
+                const int n1 = ((hi < r1 ? hi : r1) - (lo > r0 ? lo : r0)), n2 = ((hi + 1024 < r1 ? hi + 1024 : r1) - (lo + 1024 > r0 ? lo + 1024 : r0));
+                in_bytes = 4u * (unsigned)(n1 > 0 ? n1 : 0) + 8u * (unsigned)(n2 > 0 ? n2 : 0) + 4u * NX * ((has_lo ? 1u : 0u) + (has_hi ? 1u : 0u));
+        }
         if (tid == 0) {
                 mbar_init(&bars[0], 1);
                 mbar_init(&bars[1], 1);
+                mbar_init(&bars[2], 1);
+                mbar_init(&bars[3], 1);
                 fence_mbar_init();
+                mbar_arrive_expect_tx(&bars[2], in_bytes);  // armed for the first dot product
+                mbar_arrive_expect_tx(&bars[3], 4u * 32u);
         }
         for (int i = tid; i < 2 * (NB + 2) * kSlot + 4 * 16 + 3 * 32 * VWPC + 32; i += T) vp[i] = 0.0f;  // vectors, halo inboxes, dot inbox, sums
         __syncthreads();
@@ -883,6 +901,7 @@ __global__ void __launch_bounds__(ClusterGeom<P>::T, 1) k_pcg_cluster(Ctx c)
         }
 
         const unsigned a_vp = smem_u32(vp), a_vr = smem_u32(vr), a_halo = smem_u32(halo_in), a_inbox = smem_u32(inbox), a_sums = smem_u32(sums);
+        const unsigned a_mb_in = smem_u32(&bars[2]), a_mb_sum = smem_u32(&bars[3]);
         float          x_i = 0.0f;
         int            iters = 0;
         if (c.flags & F_PCG) {
@@ -897,7 +916,8 @@ __global__ void __launch_bounds__(ClusterGeom<P>::T, 1) k_pcg_cluster(Ctx c)
                 const int      vt = i_glob & 1023, rc = (vt >> 5) / VWPC, q = vt - rc * VWPC * 32;
                 const bool     second = i_glob >= 1024;
                 const unsigned post_f = mapa_cluster(a_inbox + 4u * q, rc), post_a = mapa_cluster(a_inbox + 4u * (32 * VWPC + q), rc),
-                               post_b = mapa_cluster(a_inbox + 4u * (64 * VWPC + q), rc);
+                               post_b = mapa_cluster(a_inbox + 4u * (64 * VWPC + q), rc), post_mb = mapa_cluster(a_mb_in, rc);
+                unsigned       par_in = 0, par_sum = 0;  // phase parities of the two inbox barriers
                 // the first NX threads post the first block to the CTA below, the next NX threads the last block to the CTA above
                 const bool     send_lo = has_lo && tid < NX, send_hi = has_hi && tid >= NX && tid < 2 * NX;
                 const int      hx = send_lo ? tid : tid - NX;  // element within the boundary block
@@ -905,8 +925,8 @@ __global__ void __launch_bounds__(ClusterGeom<P>::T, 1) k_pcg_cluster(Ctx c)
                 float* xch = dzbuf;  // 2 x 16 floats: this CTA's first and last block of the freshly computed vector (Ap or z)
                 auto   post_halo = [&](int kind) {
                         // kind 0: Ap, 1: z.  My first block is the "from above" halo of the CTA below; my last block the "from below" halo of the CTA above.
-                        if (send_lo) st_cluster(mapa_cluster(a_halo + 4u * ((2 * kind + 1) * 16 + hx), rank - 1), xch[hx]);
-                        if (send_hi) st_cluster(mapa_cluster(a_halo + 4u * ((2 * kind + 0) * 16 + hx), rank + 1), xch[16 + hx]);
+                        if (send_lo) st_async_cluster(mapa_cluster(a_halo + 4u * ((2 * kind + 1) * 16 + hx), rank - 1), xch[hx], mapa_cluster(a_mb_in, rank - 1));
+                        if (send_hi) st_async_cluster(mapa_cluster(a_halo + 4u * ((2 * kind + 0) * 16 + hx), rank + 1), xch[16 + hx], mapa_cluster(a_mb_in, rank + 1));
                 };
                 auto   publish_boundary = [&](float v) {
                         if (row_ok && brl == 0) xch[tid] = v;
@@ -915,19 +935,27 @@ __global__ void __launch_bounds__(ClusterGeom<P>::T, 1) k_pcg_cluster(Ctx c)
                 auto dot_post = [&](float a, float bb) {
                         if (row_ok) {
                                 if (!second)
-                                        st_cluster(post_f, fmaf(a, bb, 0.0f));
+                                        st_async_cluster(post_f, fmaf(a, bb, 0.0f), post_mb);
                                 else
-                                        st_cluster(post_a, a), st_cluster(post_b, bb);
+                                        st_async_cluster(post_a, a, post_mb), st_async_cluster(post_b, bb, post_mb);
                         }
                 };
-                // after the first barrier: the reducer warps finish the virtual threads, run the warp tree and post the sums to every CTA
+                // once this CTA's inbox is complete: the reducer warps finish the virtual threads, run the warp tree and post the sums to every CTA;
+                // then everybody waits for its table of the 32 warp sums.  One thread re-arms each barrier for the next dot product as soon as it has
+                // seen the phase complete (nobody can post into the next phase before every CTA has finished this one).
                 auto dot_reduce = [&]() {
+                        mbar_wait(&bars[2], par_in);
+                        par_in ^= 1u;
+                        if (tid == 0) mbar_arrive_expect_tx(&bars[2], in_bytes);
                         for (int vw = warp; vw < VWPC; vw += nwarps) {
                                 const int   gvw = (int)rank * VWPC + vw;
                                 const float f = inbox[32 * vw + lane], a = inbox[32 * VWPC + 32 * vw + lane], bb = inbox[64 * VWPC + 32 * vw + lane];
                                 const float sum = __shfl_sync(0xffffffffu, warp_tree(fmaf(a, bb, f)), 0);
-                                if (gvw < 32 && lane < CL) st_cluster(mapa_cluster(a_sums + 4u * gvw, lane), sum);  // lane l posts to CTA l
+                                if (gvw < 32 && lane < CL) st_async_cluster(mapa_cluster(a_sums + 4u * gvw, lane), sum, mapa_cluster(a_mb_sum, lane));  // lane l posts to CTA l
                         }
+                        mbar_wait(&bars[3], par_sum);
+                        par_sum ^= 1u;
+                        if (tid == 0) mbar_arrive_expect_tx(&bars[3], 4u * 32u);
                 };
                 if (!skip) {
                         x_i = row_ok ? lam[i_glob] : 0.0f;
@@ -956,13 +984,12 @@ __global__ void __launch_bounds__(ClusterGeom<P>::T, 1) k_pcg_cluster(Ctx c)
                         publish_boundary(z_i);
                         dot_post(r_i, z_i);
                         __syncthreads();
-                        // p halos (= z): straight into the neighbours' vp halo slots
-                        if (send_lo) st_cluster(mapa_cluster(a_vp + 4u * ((NB + 1) * kSlot + hx), rank - 1), xch[hx]);
-                        if (send_hi) st_cluster(mapa_cluster(a_vp + 4u * hx, rank + 1), xch[16 + hx]);
-                        cluster_sync();
+                        post_halo(1);  // p = z: the neighbours' boundary blocks arrive like every later z halo
                         dot_reduce();
-                        cluster_sync();
+                        if (has_lo && tid < NX) vp[tid] = halo_in[2 * 16 + tid];
+                        if (has_hi && tid >= NX && tid < 2 * NX) vp[(NB + 1) * kSlot + tid - NX] = halo_in[3 * 16 + tid - NX];
                         float rho = tree32(a_sums);
+                        __syncthreads();
                         if (!(fabsf(rho) < abs_tol)) {
                                 const float rho_init = fabsf(rho);
                                 for (int itn = 0; itn < c.max_pcg; itn++) {
@@ -972,9 +999,7 @@ __global__ void __launch_bounds__(ClusterGeom<P>::T, 1) k_pcg_cluster(Ctx c)
                                         dot_post(p_i, Ap_i);
                                         __syncthreads();
                                         post_halo(0);
-                                        cluster_sync();
                                         dot_reduce();
-                                        cluster_sync();
                                         const float alpha = rho / tree32(a_sums);
                                         x_i = fmaf(alpha, p_i, x_i);
                                         r_i = fmaf(-alpha, Ap_i, r_i);
@@ -988,9 +1013,7 @@ __global__ void __launch_bounds__(ClusterGeom<P>::T, 1) k_pcg_cluster(Ctx c)
                                         dot_post(r_i, z_i);
                                         __syncthreads();
                                         post_halo(1);
-                                        cluster_sync();
                                         dot_reduce();
-                                        cluster_sync();
                                         const float rho_new = tree32(a_sums);
 #ifdef GATO_CLUSTER_EXTRA_SYNC
                                         for (int e_ = 0; e_ < GATO_CLUSTER_EXTRA_SYNC; e_++) cluster_sync();  // measurement only: the cost of one cluster barrier
