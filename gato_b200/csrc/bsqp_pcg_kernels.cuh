@@ -743,13 +743,17 @@ __global__ void __launch_bounds__(1024, 1) k_pcg_stream(Ctx c)
 // config 4, N = 128): a THREAD-BLOCK CLUSTER of CL CTAs per solve.  CTA c keeps the rows of S and P^-1 of block rows [c*NB, (c+1)*NB) in
 // registers exactly like k_pcg (one row per thread, packed FFMA2 row trees), so the whole system (588 KB at N = 128) stays on chip for all
 // iterations -- k_pcg_stream re-reads it from L2 in every iteration, as the reference does from global memory (pcg.cuh:100,119).  What crosses
-// CTAs goes through DISTRIBUTED SHARED MEMORY (st.shared::cluster to mapa addresses) and four cluster barriers per iteration:
-//   * the window halos: one block of Ap (or z) to each neighbour ahead of the dot product's barrier; the neighbour then updates its copy of my
-//     boundary block of r (or p) itself with the same fused multiply-add, so the vector updates need no barrier of their own;
+// CTAs goes through DISTRIBUTED SHARED MEMORY as asynchronous remote stores that complete a transaction on the RECEIVER's mbarrier
+// (st.async ... mbarrier::complete_tx::bytes to mapa addresses): a CTA waits for its own inbox to fill, there is no cluster-wide barrier inside
+// the iteration (measured: a cluster barrier costs about 490 cycles here and drags a gpu-scope memory barrier along; 23.6 -> 19.1 ms on config 4):
+//   * the window halos: one block of Ap (or z) to each neighbour together with the dot-product terms; the neighbour then updates its copy of my
+//     boundary block of r (or p) itself with the same fused multiply-add, so the vector updates need no exchange of their own;
 //   * the dot products in the reference's block::dot geometry (linalg.cuh:291-327: 1024 virtual threads, virtual thread t accumulates elements
 //     t and t + 1024 in that order, warp tree, tree over the 32 warp sums): every thread posts its term -- fmaf(a, b, 0) of element t, or the
-//     operands (a, b) of element t + 1024 -- into the inbox of the CTA that reduces virtual warp t / 32 [barrier], the reducer warps finish
-//     fmaf(a', b', first), run the shuffle tree and post the warp sum into every CTA's table [barrier], and every thread folds the table.
+//     operands (a, b) of element t + 1024 -- into the inbox of the CTA that reduces virtual warp t / 32 [inbox barrier]; the reducer warps finish
+//     fmaf(a', b', first), run the shuffle tree and post the warp sum into every CTA's table [table barrier]; every thread folds the table.
+//     (Posting every term to every CTA and reducing everything locally -- one hop instead of two -- was measured slower: 20.2 vs 16.2 ms in
+//     k_pcg_cluster on config 4; the remote mbarrier transactions are the cost, not the hops.)
 // The rows and the primal step's operands arrive through the TMA unit (cp.async.bulk + mbarrier).  P^-1 is read complete: its off-diagonal blocks
 // are built beforehand by k_pcg_stream's K2 phase (once per SQP iteration).
 // -----------------------------------------------------------------------------------------------------
