@@ -98,6 +98,18 @@ struct gato_solver {
         float *          h_kkt_qmax = nullptr, *h_kkt_cmax = nullptr;
         bool             kkt_log = false;
         DevArr<float>    ee_q, ee_out;  // staging of gato_ee_pos
+        // CUDA graphs of the solve's launch sequence for small batches (the MPC regime is launch-latency bound): one instantiated graph per
+        // distinct (xu, x_s, ref pointers, dt, switches); replayed while the caller keeps passing the same device buffers
+        struct GraphEntry {
+                float*          xu;
+                const float *   xs, *ref;
+                float           dt;
+                int             adapt, kkt_log;
+                long            launches;
+                cudaGraphExec_t exec;
+        };
+        std::vector<GraphEntry> graphs;
+        bool                    use_graph = false;
         DevArr<unsigned> num_solved, num_unsolved, pcg_done;
         bool             overlap = true;  // merit / line search overlapped with the tail of k_pcg (GATO_NO_OVERLAP=1 switches it off)
         DevArr<float>    st_xu, st_xs, st_ref, st_xkp1, st_xk, st_uk;  // staging for *_host calls
@@ -267,7 +279,7 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
                 launch_pcg<P>(s, c);
                 // the register-resident k_pcg hands solves over one by one: the line search may start under its last wave (not with per-kernel timing,
                 // whose events serialise the launches)
-                const bool ov = s->overlap && !s->timing && s->pcg_rpt == 0;
+                const bool ov = s->overlap && !s->timing && s->pcg_rpt == 0 && !s->use_graph;  // (graphs are for batches that have no wave tail to fill)
                 c.flags = F_CHECK_STOP | F_MERIT | F_LS | (ov ? F_OVERLAP : 0);
                 launch_merit<P, kNumAlphas>(s, c);
         }
@@ -295,9 +307,48 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
         return GATO_OK;
 }
 
-int dispatch_enqueue(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref, float dt)
+int enqueue_direct(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref, float dt)
 {
         return s->plant == GATO_PLANT_IIWA14 ? enqueue_solve<Iiwa14>(s, d_xu, d_xs, d_ref, dt) : enqueue_solve<Indy7>(s, d_xu, d_xs, d_ref, dt);
+}
+
+// Small batches: the same sequence (memsets, 4 * iterations + 1 kernels, the side-stream fork / join, the copies of the statistics to pinned
+// memory) captured once into a CUDA graph and replayed with one launch.  Any failure of the capture falls back to direct enqueueing.
+int dispatch_enqueue(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref, float dt)
+{
+        if (!s->use_graph || s->timing) return enqueue_direct(s, d_xu, d_xs, d_ref, dt);
+        const int adapt = s->adapt_rho ? 1 : 0, klog = s->kkt_log ? 1 : 0;
+        for (auto& e : s->graphs)
+                if (e.xu == d_xu && e.xs == d_xs && e.ref == d_ref && e.dt == dt && e.adapt == adapt && e.kkt_log == klog) {
+                        CUDA_TRY(s, cudaGraphLaunch(e.exec, s->stream));
+                        s->launches += e.launches;
+                        return GATO_OK;
+                }
+        const long l0 = s->launches;
+        if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();
+                s->use_graph = false;
+                return enqueue_direct(s, d_xu, d_xs, d_ref, dt);
+        }
+        const int       rc = enqueue_direct(s, d_xu, d_xs, d_ref, dt);
+        cudaGraph_t     graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t     ce = cudaStreamEndCapture(s->stream, &graph);
+        if (rc == GATO_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != GATO_OK || ce != cudaSuccess || !exec) {
+                cudaGetLastError();
+                s->use_graph = false;  // not capturable here: enqueue directly from now on
+                s->launches = l0;
+                return enqueue_direct(s, d_xu, d_xs, d_ref, dt);
+        }
+        if (s->graphs.size() >= 4) {
+                cudaGraphExecDestroy(s->graphs.front().exec);
+                s->graphs.erase(s->graphs.begin());
+        }
+        s->graphs.push_back({d_xu, d_xs, d_ref, dt, adapt, klog, s->launches - l0, exec});
+        CUDA_TRY(s, cudaGraphLaunch(exec, s->stream));
+        return GATO_OK;
 }
 
 int fill_stats(gato_solver* s, gato_stats* st)
@@ -460,6 +511,8 @@ int gato_create(gato_solver** out, int plant, int N, int B, int device, void* st
         }
         s->h_sqp_iters.assign(B, 0);
         s->overlap = !getenv("GATO_NO_OVERLAP");
+        // graphs for the regime where the launches, not the kernels, set the latency (the split line-search kernel's regime: no overlapped launch inside)
+        s->use_graph = B <= 148 && !getenv("GATO_NO_GRAPH");
         // per-batch hyper-parameters  (bsqp.cuh:48-58)
         std::vector<float> rho0(B, prm->rho), drho0(B, 1.0f), mu(B, prm->mu), tol(B, prm->pcg_tol);
         cudaMemcpy(s->rho.p, rho0.data(), sizeof(float) * B, cudaMemcpyHostToDevice);
@@ -494,6 +547,7 @@ void gato_destroy(gato_solver* s)
         for (void* p : {(void*)s->h_mpc_in, (void*)s->h_mpc_best, (void*)s->h_mpc_err, (void*)s->h_mpc_id, (void*)s->h_mpc_gerr})
                 if (p) cudaFreeHost(p);
         for (cudaEvent_t e : s->tick_ev) cudaEventDestroy(e);
+        for (auto& e : s->graphs) cudaGraphExecDestroy(e.exec);
         if (s->side) cudaStreamSynchronize(s->side), cudaStreamDestroy(s->side);
         if (s->ev_fork) cudaEventDestroy(s->ev_fork);
         if (s->ev_join) cudaEventDestroy(s->ev_join);
