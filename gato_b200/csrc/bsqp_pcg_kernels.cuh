@@ -191,6 +191,13 @@ __device__ __forceinline__ float2 lds64(unsigned a)
         return v;
 }
 __device__ __forceinline__ void sts32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+// a shared address the compiler cannot see through: it stays in a register across the loop (otherwise `window base + constant` is re-derived)
+__device__ __forceinline__ unsigned opaque_addr(unsigned a)
+{
+        unsigned r;
+        asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+        return r;
+}
 
 // (M v)[row] with the reference's reduction tree (btdMatrixVectorProduct, linalg.cuh:197-216: lane l accumulates columns l and l+32, then
 // the shuffle tree 16, 8, 4, 2, 1), evaluated by ONE thread on PACKED pairs: Blackwell's FFMA2 / FADD2 (fma.rn.f32x2, add.rn.f32x2) work
@@ -429,9 +436,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_pcg(Ctx c)
                 const float  eps = c.pcg_tol[b];
                 const float  abs_tol = 1e-6f;
                 const bool   skip = c.conv[b] != 0;  // pcg.cuh:29-32
-                const unsigned wp = smem_u32(vp + br * kSlot), wr = smem_u32(vr + br * kSlot);  // this row's window: padded blocks br .. br+2
-                const unsigned own_p = smem_u32(vp + own), own_r = smem_u32(vr + own);
-                const unsigned sA = smem_u32(scratchA), sB = smem_u32(scratchB);
+                const unsigned wp = opaque_addr(smem_u32(vp + br * kSlot)), wr = opaque_addr(smem_u32(vr + br * kSlot));  // this row's window: padded blocks br .. br+2
+                const unsigned own_p = opaque_addr(smem_u32(vp + own)), own_r = opaque_addr(smem_u32(vr + own));
+                const unsigned sA = opaque_addr(smem_u32(scratchA)), sB = opaque_addr(smem_u32(scratchB));
                 const unsigned my_prod = smem_u32(prod + tid), row_prod = smem_u32(prod + 32 * warp);
                 // dot, phase 1 (before the CTA barrier): the warp's partial sum -> scratch[warp]
                 auto dot_partial = [&](float term, unsigned scratch) {

@@ -59,6 +59,64 @@ static void stage_kkt(int N, int B, const float* xu, const float* xs, const floa
                 }
 }
 
+// the same stage through the code paths the KERNELS run: k_kkt's rolled halves (linearize_half_rolled<0/1>) when variant == 1, k_kkt_fine's
+// per-column pieces (dyn_prologue + linearize_base + linearize_column) when variant == 2
+template<class P>
+static void stage_kkt_kernel_paths(int variant, int N, int B, const float* xu, const float* fext, float dt, float* A, float* Bm, float* c)
+{
+        constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ;
+        const int     traj = (NX + NU) * N - NU;
+        for (int b = 0; b < B; b++)
+                for (int k = 0; k < N - 1; k++) {
+                        const float* xux = xu + (size_t)b * traj + k * (NX + NU);
+                        float*       Ak = A + ((size_t)b * N + k) * NX * NX;
+                        float*       Bk = Bm + ((size_t)b * N + k) * NX * NU;
+                        float*       ck = c + ((size_t)b * N + k + 1) * NX;
+                        if (variant == 1) {
+                                Items<P>::template linearize_half_rolled<0>(xux, fext + 6 * b, dt, [&](int e, float v) { Ak[e] = v; }, [&](int, float) {}, [&](int e, float v) { ck[e] = v; });
+                                Items<P>::template linearize_half_rolled<1>(xux, fext + 6 * b, dt, [&](int e, float v) { Ak[e] = v; }, [&](int e, float v) { Bk[e] = v; }, [&](int, float) {});
+                        } else {
+                                typename Rbd<P>::DynState st;
+                                Rbd<P>::dyn_prologue(xux, xux + NQ, xux + NX, fext + 6 * b, st);
+                                Items<P>::linearize_base(st, xux, dt, [&](int e, float v) { Bk[e] = v; }, [&](int e, float v) { ck[e] = v; });
+                                sfor<0, NX>([&](auto cc) {
+                                        constexpr int cidx = cc;
+                                        Items<P>::template linearize_column<cidx / NQ, cidx % NQ>(st, xux + NQ, dt, [&](int e, float v) { Ak[e] = v; });
+                                });
+                        }
+                }
+}
+
+// the split merit kernel's halves: merit = fmaf(mu, merit_mid_cons, tracking_cost)
+template<class P>
+static void stage_merit_split(int N, int B, const float* xu, const float* dz, const float* xs, const float* ref, const float* mu, const float* fext, float dt, const float* c7, int na, float* merit)
+{
+        constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ;
+        const int     traj = (NX + NU) * N - NU;
+        const Costs   cs{c7[0], c7[1], c7[2], c7[3], c7[4], c7[5], c7[6]};
+        for (int b = 0; b < B; b++)
+                for (int a = 0; a < na; a++) {
+                        const float alpha = (float)(1.0 / (double)(1 << a));
+                        float       m = 0.0f;
+                        for (int k = 0; k < N; k++) {
+                                float        xux[2 * NX + NU];
+                                const int    cnt = (k == N - 1) ? NX : 2 * NX + NU;
+                                const float *xk = xu + (size_t)b * traj + k * (NX + NU), *dk = dz + (size_t)b * traj + k * (NX + NU);
+                                for (int i = 0; i < cnt; i++) xux[i] = fmaf(alpha, dk[i], xk[i]);
+                                float mk;
+                                if (k < N - 1)
+                                        mk = fmaf(mu[b], Items<P>::merit_mid_cons(xux, fext + 6 * b, dt), Items<P>::template tracking_cost<false>(xux, ref + (size_t)b * 6 * N + 6 * k, cs));
+                                else {
+                                        float e0[NX];
+                                        for (int i = 0; i < NX; i++) e0[i] = fabsf(fmaf(alpha, dz[(size_t)b * traj + i], xu[(size_t)b * traj + i]) - xs[(size_t)b * NX + i]);
+                                        mk = fmaf(mu[b], Items<P>::merit_last_cons(e0), Items<P>::template tracking_cost<true>(xux, ref + (size_t)b * 6 * N + 6 * k, cs));
+                                }
+                                m = m + mk;
+                        }
+                        merit[b * na + a] = m;
+                }
+}
+
 template<class P>
 static void stage_merit(int N, int B, const float* xu, const float* dz, const float* xs, const float* ref, const float* mu, const float* fext, float dt, const float* c7, int na, float* merit)
 {
@@ -104,6 +162,23 @@ int hostchk_stage_kkt(int plant, int N, int B, const float* xu, const float* xs,
                 stage_kkt<Iiwa14>(N, B, xu, xs, ref, fext, dt, cost7, Q, R, q, r, A, Bm, c);
         else
                 stage_kkt<Indy7>(N, B, xu, xs, ref, fext, dt, cost7, Q, R, q, r, A, Bm, c);
+        return 0;
+}
+int hostchk_stage_kkt_kernel_paths(int plant, int variant, int N, int B, const float* xu, const float* fext, float dt, float* A, float* Bm, float* c)
+{
+        if (plant == 1)
+                stage_kkt_kernel_paths<Iiwa14>(variant, N, B, xu, fext, dt, A, Bm, c);
+        else
+                stage_kkt_kernel_paths<Indy7>(variant, N, B, xu, fext, dt, A, Bm, c);
+        return 0;
+}
+int hostchk_stage_merit_split(int plant, int N, int B, const float* xu, const float* dz, const float* xs, const float* ref, const float* mu, const float* fext, float dt, const float* cost7, int na,
+                              float* merit)
+{
+        if (plant == 1)
+                stage_merit_split<Iiwa14>(N, B, xu, dz, xs, ref, mu, fext, dt, cost7, na, merit);
+        else
+                stage_merit_split<Indy7>(N, B, xu, dz, xs, ref, mu, fext, dt, cost7, na, merit);
         return 0;
 }
 int hostchk_stage_merit(int plant, int N, int B, const float* xu, const float* dz, const float* xs, const float* ref, const float* mu, const float* fext, float dt, const float* cost7, int na,

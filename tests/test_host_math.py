@@ -20,6 +20,8 @@ def hostlib(oracle_built):
     lib.hostchk_dyn_dump.argtypes = [C.c_int, C.c_int] + [f32p] * 7
     lib.hostchk_stage_kkt.argtypes = [C.c_int] * 3 + [f32p] * 4 + [C.c_float, f32p] + [f32p] * 7
     lib.hostchk_stage_merit.argtypes = [C.c_int] * 3 + [f32p] * 6 + [C.c_float, f32p, C.c_int, f32p]
+    lib.hostchk_stage_merit_split.argtypes = [C.c_int] * 3 + [f32p] * 6 + [C.c_float, f32p, C.c_int, f32p]
+    lib.hostchk_stage_kkt_kernel_paths.argtypes = [C.c_int] * 4 + [f32p] * 2 + [C.c_float] + [f32p] * 3
     return lib
 
 
@@ -48,6 +50,12 @@ def test_product_item_math_bit_exact(hostlib, plant, N, cfg):
     hostlib.hostchk_stage_kkt(pid, N, B, xu.ravel(), w["xs"].ravel(), w["ref"].ravel(), fext.ravel(), np.float32(w["dt"]), cost7(p), *[k1[k].reshape(-1) for k in ("Q", "R", "q", "r", "A", "Bm", "c")])
     for k in k0:
         assert n_mismatch(k1[k], k0[k]) == 0, k
+    # the code paths the kernels run: k_kkt's rolled halves (1) and k_kkt_fine's prologue + base + columns (2)
+    for variant in (1, 2):
+        k2 = {k: np.zeros_like(k0[k]) for k in ("A", "Bm", "c")}
+        hostlib.hostchk_stage_kkt_kernel_paths(pid, variant, N, B, xu.ravel(), fext.ravel(), np.float32(w["dt"]), *[k2[k].reshape(-1) for k in ("A", "Bm", "c")])
+        assert n_mismatch(k2["A"][:, :-1], k0["A"][:, :-1]) == 0 and n_mismatch(k2["Bm"][:, :-1], k0["Bm"][:, :-1]) == 0, variant
+        assert n_mismatch(k2["c"][:, 1:], k0["c"][:, 1:]) == 0, variant
     dz = rng.normal(0, 0.05, xu.shape).astype(np.float32)
     mu = np.full(B, 10, np.float32)
     for na in (1, 8):
@@ -55,6 +63,9 @@ def test_product_item_math_bit_exact(hostlib, plant, N, cfg):
         m1 = np.zeros_like(m0)
         hostlib.hostchk_stage_merit(pid, N, B, xu.ravel(), dz.ravel(), w["xs"].ravel(), w["ref"].ravel(), mu, fext.ravel(), np.float32(w["dt"]), cost7(p), na, m1.reshape(-1))
         assert n_mismatch(m1, m0) == 0
+        m2 = np.zeros_like(m0)
+        hostlib.hostchk_stage_merit_split(pid, N, B, xu.ravel(), dz.ravel(), w["xs"].ravel(), w["ref"].ravel(), mu, fext.ravel(), np.float32(w["dt"]), cost7(p), na, m2.reshape(-1))
+        assert n_mismatch(m2, m0) == 0
 
 
 def test_linearisation_matches_finite_differences(oracle_built):
