@@ -173,27 +173,33 @@ struct Items {
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
-                for (int k = 0; k < NQ; k++) {
-                        float dc[NQ], d[NQ];
-                        R::template rnea_grad_col_rt<HALF>(k, st.X, xux + NQ, st.v, st.a, st.f, st.Iv, st.FxvI, dc);
+                for (int k0 = 0; k0 < NQ; k0 += 2) {
+                        // two columns per pass as the lanes of packed pairs (rnea_grad_col2_rt); with NQ odd the last pass has one
+                        f2 dc[NQ], d[NQ];
+                        R::template rnea_grad_col2_rt<HALF>(k0, st.X, xux + NQ, st.v, st.a, st.f, st.Iv, st.FxvI, dc);
                         sfor<0, NQ>([&](auto rc) {
                                 constexpr int row = rc;
-                                float         val = 0.0f;
-                                sfor<0, NQ>([&](auto cc) { val = fmaf(R::template minv_sym<row, cc>(st.Minv), dc[cc], val); });
-                                d[row] = -val;
+                                f2            val = mk2(0.0f, 0.0f);
+                                sfor<0, NQ>([&](auto cc) { val = fma2s(R::template minv_sym<row, cc>(st.Minv), dc[cc], val); });
+                                d[row] = neg2(val);
                         });
-                        const int c = k + HALF * NQ;
-                        sfor<0, NX>([&](auto rc) {
-                                constexpr int r = rc, rd = r % NQ;
-                                float         val = (r == c) ? 1.0f : 0.0f;
-                                if constexpr (r < NQ) {
-                                        if (HALF == 1 && r == k) val = val + dt;  // c >= NQ && r == c - NQ
-                                        val = fmaf(dt_sq_half, d[rd], val);
-                                } else {
-                                        val = fmaf(dt, d[rd], val);
-                                }
-                                putA(c * NX + r, val);
-                        });
+                        for (int l = 0; l < 2; l++) {
+                                const int k = k0 + l;
+                                if (k >= NQ) break;
+                                const int c = k + HALF * NQ;
+                                sfor<0, NX>([&](auto rc) {
+                                        constexpr int r = rc, rd = r % NQ;
+                                        const float   dd = l == 0 ? d[rd].x : d[rd].y;
+                                        float         val = (r == c) ? 1.0f : 0.0f;
+                                        if constexpr (r < NQ) {
+                                                if (HALF == 1 && r == k) val = val + dt;  // c >= NQ && r == c - NQ
+                                                val = fmaf(dt_sq_half, dd, val);
+                                        } else {
+                                                val = fmaf(dt, dd, val);
+                                        }
+                                        putA(c * NX + r, val);
+                                });
+                        }
                 }
                 if constexpr (HALF == 0) {
                         float qn[NQ], qdn[NQ];

@@ -44,6 +44,51 @@ GATO_HD float g_cos(float x) { return cosf(x); }
 GATO_HD float g_log(float x) { return logf(x); }
 #endif
 
+// ---- packed pairs ----------------------------------------------------------------------------------
+// Two fp32 lanes through ONE instruction: Blackwell's FFMA2 / FADD2 / FMUL2 (fma.rn.f32x2 ...) round each lane exactly like the scalar
+// operation, so "two vectors through the same matrix" costs half the instructions with bit-identical results -- what matters for kernels
+// that are bound by instruction fetch and issue.  The host build (tests) evaluates the two lanes one after the other.
+#if defined(__CUDACC__)
+using f2 = float2;
+#else
+struct f2 {
+        float x, y;
+};
+#endif
+GATO_HD f2 mk2(float x, float y)
+{
+        f2 r;
+        r.x = x, r.y = y;
+        return r;
+}
+#ifndef GATO_F2_EMULATE
+#define GATO_F2_EMULATE 0  // debugging aid: bit 0 / 1 / 2 evaluate fma2 / add2 / mul2 lane by lane with scalar instructions on the device too
+#endif
+GATO_HD f2 fma2(f2 a, f2 b, f2 c)
+{
+#if defined(__CUDA_ARCH__) && !(GATO_F2_EMULATE & 1)
+        return __ffma2_rn(a, b, c);
+#else
+        return mk2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+GATO_HD f2 fma2s(float s, f2 b, f2 c) { return fma2(mk2(s, s), b, c); }  // scalar coefficient, broadcast
+GATO_HD f2 add2(f2 a, f2 b)
+{
+#if defined(__CUDA_ARCH__) && !(GATO_F2_EMULATE & 2)
+        return __fadd2_rn(a, b);
+#else
+        return mk2(a.x + b.x, a.y + b.y);
+#endif
+}
+// The product is evaluated as two SCALAR multiplies on purpose.  ptxas 12.9 fuses a packed multiply with a following packed add into one
+// FFMA2 -- even when the PTX says mul.rn.f32x2 / add.rn.f32x2 with explicit rounding modifiers, which forbid contraction, and even under
+// -fmad=false (seen in SASS; it also folds fma.rn.f32x2(a, b, -0.0) back into a multiply first).  One rounding instead of two changes last
+// bits against the scalar path and the oracle (found as 1-ulp differences in A between k_kkt and k_kkt_fine).  Scalar FMUL + FADD2 is left alone.
+GATO_HD f2 mul2(f2 a, f2 b) { return mk2(a.x * b.x, a.y * b.y); }
+GATO_HD f2 mul2s(float s, f2 b) { return mul2(mk2(s, s), b); }
+GATO_HD f2 neg2(f2 a) { return mk2(-a.x, -a.y); }
+
 constexpr float kGravity = 9.81f;  // iiwa14_plant.cuh:25-28
 
 // ---- robot description -----------------------------------------------------------------------------
@@ -193,6 +238,55 @@ struct Rbd {
                 });
                 return r;
         }
+        // the same three products for a PAIR of vectors (lane x and lane y of every entry): identical chains, one packed instruction per term
+        template<int J, int R>
+        static GATO_HD f2 xrow2(const Xmat& X, const f2 (&v)[6])
+        {
+                f2 r = mk2(0.0f, 0.0f);
+                sfor<0, 6>([&](auto ic) {
+                        constexpr int i = ic;
+                        if constexpr (XE<P, J, R, i>::nz) r = fma2s(xv<J, R, i>(X), v[i], r);
+                });
+                return r;
+        }
+        template<int J, int C>
+        static GATO_HD f2 xcol2(const Xmat& X, const f2 (&f)[6])
+        {
+                f2 r = mk2(0.0f, 0.0f);
+                sfor<0, 6>([&](auto ic) {
+                        constexpr int i = ic;
+                        if constexpr (XE<P, J, i, C>::nz) r = fma2s(xv<J, i, C>(X), f[i], r);
+                });
+                return r;
+        }
+        template<int J, int R>
+        static GATO_HD f2 irow2(const f2 (&v)[6])
+        {
+                f2 r = mk2(0.0f, 0.0f);
+                sfor<0, 6>([&](auto ic) {
+                        constexpr int i = ic;
+                        if constexpr (inertia<P, J, R, i>() != 0.0f) r = fma2s(inertia<P, J, R, i>(), v[i], r);
+                });
+                return r;
+        }
+        // fx(f) * t for a pair of f and one t (the lanes of f are two gradient columns, t = I v of the joint)
+        static GATO_HD void fx2_times_v(f2 (&r)[6], const f2 (&f)[6], const float (&t)[6])
+        {
+                f2 s;
+                s = fma2s(t[2], f[1], neg2(mul2s(t[1], f[2])));
+                s = fma2s(t[4], neg2(f[5]), s);
+                r[0] = fma2s(t[5], f[4], s);
+                s = fma2s(t[0], f[2], neg2(mul2s(t[2], f[0])));
+                s = fma2s(t[3], f[5], s);
+                r[1] = fma2s(t[5], neg2(f[3]), s);
+                s = fma2s(t[1], f[0], neg2(mul2s(t[0], f[1])));
+                s = fma2s(t[3], neg2(f[4]), s);
+                r[2] = fma2s(t[4], f[3], s);
+                r[3] = fma2s(t[5], f[1], neg2(mul2s(t[4], f[2])));
+                r[4] = fma2s(t[3], f[2], neg2(mul2s(t[5], f[0])));
+                r[5] = fma2s(t[4], f[0], neg2(mul2s(t[3], f[1])));
+        }
+
         // fx(f) * t   (iiwa14_grid.cuh:896-905) with the fma placement nvcc emits for it
         static GATO_HD void fx_times_v(float (&r)[6], const float (&f)[6], const float (&t)[6])
         {
@@ -505,6 +599,95 @@ struct Rbd {
                                 }
                         }
                         sfor<0, 6>([&](auto rc) { df[j - 1][rc] = df[j - 1][rc] + upd[rc]; });
+                });
+                sfor<0, NQ>([&](auto jc) { dc[jc] = df[jc][2]; });
+        }
+
+        // TWO columns k0 and k0 + 1 at a time, as the two lanes of packed pairs (dc[j].x = d c_j / d{q|qd}_k0, dc[j].y = ... k0+1).  Every operation
+        // of rnea_grad_col_rt is "a coefficient times a column's vector": the coefficient is shared and the two columns ride in one packed
+        // instruction.  Column k0 + 1 starts one joint later; until then its lane carries exact zeros, which change nothing downstream (every
+        // chain starts from +0).  With k0 + 1 == NQ the second lane stays zero and is ignored by the caller.
+        template<int W>
+        static GATO_HD void rnea_grad_col2_rt(int k0, const Xmat& X, const float* qd, const V6& v, const V6& a, const V6& f, const V6& Iv, const float (&FxvI)[NQ][36], f2 (&dc)[NQ])
+        {
+                f2 df[NQ][6];
+                f2 dv[6], da[6];
+                const f2 z2 = mk2(0.0f, 0.0f);
+                sfor<0, NQ>([&](auto jc) { sfor<0, 6>([&](auto rc) { df[jc][rc] = z2; }); });
+                sfor<0, 6>([&](auto rc) { dv[rc] = z2, da[rc] = z2; });
+                sfor<0, NQ>([&](auto jc) {
+                        constexpr int j = jc;
+                        if (j >= k0) {
+                                f2 ndv[6], nda[6];
+                                sfor<0, 6>([&](auto rc) { ndv[rc] = z2, nda[rc] = z2; });
+                                if constexpr (j > 0) {
+                                        if (j > k0) {
+                                                // propagate the columns that have started (lane y still carries zeros at j == k0 + 1: they stay zeros)
+                                                sfor<0, 6>([&](auto rc) { ndv[rc] = xrow2<j, rc>(X, dv); });
+                                                nda[0] = mul2s(qd[j], ndv[1]), nda[1] = mul2s(qd[j], neg2(ndv[0])), nda[2] = z2;
+                                                nda[3] = mul2s(qd[j], ndv[4]), nda[4] = mul2s(qd[j], neg2(ndv[3])), nda[5] = z2;
+                                                sfor<0, 6>([&](auto rc) { nda[rc] = add2(nda[rc], xrow2<j, rc>(X, da)); });
+                                        }
+                                }
+                                if (j == k0 || j == k0 + 1) {
+                                        // the column that starts at this joint (scalar): dv = mx2(X v_parent) | S ; da = mx2_scaled(dv, qd) + { mx2(X a_parent) | mx2(v) }
+                                        float sdv[6], sda[6], src[6];
+                                        if constexpr (W == 0) {
+                                                float Xv[6], Xa[6];
+                                                sfor<0, 6>([&](auto rc) {
+                                                        constexpr int row = rc;
+                                                        if constexpr (j == 0) {
+                                                                Xv[row] = 0.0f;
+                                                                Xa[row] = XE<P, 0, row, 5>::nz ? xv<0, row, 5>(X) * kGravity : 0.0f;
+                                                        } else {
+                                                                Xv[row] = xrow<j, row>(X, v[j > 0 ? j - 1 : 0]);
+                                                                Xa[row] = xrow<j, row>(X, a[j > 0 ? j - 1 : 0]);
+                                                        }
+                                                });
+                                                sdv[0] = Xv[1], sdv[1] = -Xv[0], sdv[2] = 0.0f, sdv[3] = Xv[4], sdv[4] = -Xv[3], sdv[5] = 0.0f;
+                                                src[0] = Xa[1], src[1] = -Xa[0], src[2] = 0.0f, src[3] = Xa[4], src[4] = -Xa[3], src[5] = 0.0f;
+                                                if constexpr (j == 0) sfor<0, 6>([&](auto rc) { sdv[rc] = 0.0f; });
+                                        } else {
+                                                sfor<0, 6>([&](auto rc) { sdv[rc] = (rc == 2) ? 1.0f : 0.0f; });
+                                                src[0] = v[j][1], src[1] = -v[j][0], src[2] = 0.0f, src[3] = v[j][4], src[4] = -v[j][3], src[5] = 0.0f;
+                                        }
+                                        sda[0] = sdv[1] * qd[j], sda[1] = (-sdv[0]) * qd[j], sda[2] = 0.0f, sda[3] = sdv[4] * qd[j], sda[4] = (-sdv[3]) * qd[j], sda[5] = 0.0f;
+                                        sfor<0, 6>([&](auto rc) { sda[rc] = sda[rc] + src[rc]; });
+                                        if (j == k0)
+                                                sfor<0, 6>([&](auto rc) { ndv[rc].x = sdv[rc], nda[rc].x = sda[rc]; });
+                                        else
+                                                sfor<0, 6>([&](auto rc) { ndv[rc].y = sdv[rc], nda[rc].y = sda[rc]; });
+                                }
+                                sfor<0, 6>([&](auto rc) {
+                                        dv[rc] = ndv[rc];
+                                        da[rc] = nda[rc];
+                                });
+                                // df_j = fx(dv) I v  +  ( I da + (fx(v) I) dv )
+                                f2 t0[6];
+                                fx2_times_v(t0, dv, Iv[j]);
+                                sfor<0, 6>([&](auto rc) {
+                                        constexpr int row = rc;
+                                        const f2      d1 = irow2<j, row>(da);
+                                        f2            d2 = z2;
+                                        sfor<0, 6>([&](auto tc) { d2 = fma2s(FxvI[j][row + 6 * tc], dv[tc], d2); });
+                                        df[j][row] = add2(t0[row], add2(d1, d2));
+                                });
+                        }
+                });
+                sfor_down<1, NQ>([&](auto jc) {
+                        constexpr int j = jc;
+                        f2            upd[6];
+                        sfor<0, 6>([&](auto rc) { upd[rc] = xcol2<j, rc>(X, df[j]); });
+                        if constexpr (W == 0) {
+                                if (j == k0 || j == k0 + 1) {
+                                        float mxf[6] = {f[j][1], -f[j][0], 0.0f, f[j][4], -f[j][3], 0.0f};
+                                        if (j == k0)
+                                                sfor<0, 6>([&](auto rc) { upd[rc].x = upd[rc].x + (-xcol<j, rc>(X, mxf)); });
+                                        else
+                                                sfor<0, 6>([&](auto rc) { upd[rc].y = upd[rc].y + (-xcol<j, rc>(X, mxf)); });
+                                }
+                        }
+                        sfor<0, 6>([&](auto rc) { df[j - 1][rc] = add2(df[j - 1][rc], upd[rc]); });
                 });
                 sfor<0, NQ>([&](auto jc) { dc[jc] = df[jc][2]; });
         }

@@ -160,3 +160,19 @@ def test_cluster_pcg_kernel_long_horizons(backends, plant, N, monkeypatch):
     p2 = dict(p, max_sqp_iters=1, max_pcg_iters=25, pcg_tol=-1.0)
     ro, rg = o.solver(B, p2).solve(w["xu"], w["xs"], w["ref"], w["dt"]), g.solver(B, p2).solve(w["xu"], w["xs"], w["ref"], w["dt"])
     assert (rg["pcg_iters"] == 25).all() and n_mismatch(rg["XU"], ro["XU"]) == 0
+
+
+@pytest.mark.parametrize("plant", ["iiwa14", "indy7"])
+def test_kkt_large_grid_path_bit_exact(backends, plant):
+    """k_kkt (the large-grid kernel: rolled halves, two gradient columns per pass as the lanes of packed FFMA2 pairs) against the oracle at stage
+    level; the small stage tests all take k_kkt_fine.  (This is the test that would have caught ptxas fusing mul.rn.f32x2 + add.rn.f32x2.)"""
+    o, g = backends(plant, 32)
+    B = 80  # 80 x 32 items: beyond k_kkt_fine's grid limit
+    w = make_config(2 if plant == "iiwa14" else 3, B=B, N=32)
+    rng = np.random.default_rng(1)
+    xu = (w["xu"] + rng.normal(0, 0.3, w["xu"].shape)).astype(np.float32)
+    fext = rng.normal(0, 2, (B, 6)).astype(np.float32)
+    p = dict(w["params"], vel_lim_cost=0.002, ctrl_lim_cost=0.001)
+    ko, kg = o.stage_kkt(B, xu, w["xs"], w["ref"], fext, w["dt"], p), g.stage_kkt(B, xu, w["xs"], w["ref"], fext, w["dt"], p)
+    for k in ko:
+        assert n_mismatch(kg[k], ko[k]) == 0, k
