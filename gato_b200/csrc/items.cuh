@@ -276,8 +276,12 @@ struct Items {
                         constexpr int i = ic;
                         const float   err = xu[i + NQ];
                         float         c = ((0.5f * cs.qd_cost) * err) * err;
-                        c = fmaf(cs.q_lim_cost, R::joint_barrier(xu[i], limit<P, 0, i, 0>(), limit<P, 0, i, 1>()), c);
-                        c = fmaf(cs.vel_lim_cost, R::joint_barrier(xu[i + NQ], limit<P, 1, i, 0>(), limit<P, 1, i, 1>()), c);
+                        // A barrier whose weight is exactly zero is not evaluated (two logarithms each; the default parameters have vel_lim_cost =
+                        // ctrl_lim_cost = 0): fmaf(0, barrier, c) == c bit for bit for every finite barrier value -- the clamped logarithms are finite for
+                        // every finite state, and c >= +0 here -- and a NaN state still reaches the sum through the quadratic terms / the end-effector
+                        // position.  (Only an infinite state entry under a zero weight would give NaN instead of the skipped term.)
+                        if (cs.q_lim_cost != 0.0f) c = fmaf(cs.q_lim_cost, R::joint_barrier(xu[i], limit<P, 0, i, 0>(), limit<P, 0, i, 1>()), c);
+                        if (cs.vel_lim_cost != 0.0f) c = fmaf(cs.vel_lim_cost, R::joint_barrier(xu[i + NQ], limit<P, 1, i, 0>(), limit<P, 1, i, 1>()), c);
                         cv[i] = c;
                 });
                 if constexpr (!LAST) {
@@ -285,7 +289,7 @@ struct Items {
                                 constexpr int j = jc;
                                 const float   err = xu[NX + j];
                                 float         c = ((0.5f * cs.u_cost) * err) * err;
-                                c = fmaf(cs.ctrl_lim_cost, R::joint_barrier(xu[NX + j], limit<P, 2, j, 0>(), limit<P, 2, j, 1>()), c);
+                                if (cs.ctrl_lim_cost != 0.0f) c = fmaf(cs.ctrl_lim_cost, R::joint_barrier(xu[NX + j], limit<P, 2, j, 0>(), limit<P, 2, j, 1>()), c);
                                 cv[NQ + j] = c;
                         });
                 }

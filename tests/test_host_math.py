@@ -58,13 +58,14 @@ def test_product_item_math_bit_exact(hostlib, plant, N, cfg):
         assert n_mismatch(k2["c"][:, 1:], k0["c"][:, 1:]) == 0, variant
     dz = rng.normal(0, 0.05, xu.shape).astype(np.float32)
     mu = np.full(B, 10, np.float32)
-    for na in (1, 8):
-        m0 = be.stage_merit(B, xu, dz, w["xs"], w["ref"], mu, fext, w["dt"], p, na)
+    # every barrier weight non-zero, then the default weights (zero velocity / control barriers are skipped by the product, not by the oracle)
+    for na, pm in ((1, p), (8, p), (8, dict(w["params"])), (8, dict(w["params"], q_lim_cost=0.0))):
+        m0 = be.stage_merit(B, xu, dz, w["xs"], w["ref"], mu, fext, w["dt"], pm, na)
         m1 = np.zeros_like(m0)
-        hostlib.hostchk_stage_merit(pid, N, B, xu.ravel(), dz.ravel(), w["xs"].ravel(), w["ref"].ravel(), mu, fext.ravel(), np.float32(w["dt"]), cost7(p), na, m1.reshape(-1))
+        hostlib.hostchk_stage_merit(pid, N, B, xu.ravel(), dz.ravel(), w["xs"].ravel(), w["ref"].ravel(), mu, fext.ravel(), np.float32(w["dt"]), cost7(pm), na, m1.reshape(-1))
         assert n_mismatch(m1, m0) == 0
         m2 = np.zeros_like(m0)
-        hostlib.hostchk_stage_merit_split(pid, N, B, xu.ravel(), dz.ravel(), w["xs"].ravel(), w["ref"].ravel(), mu, fext.ravel(), np.float32(w["dt"]), cost7(p), na, m2.reshape(-1))
+        hostlib.hostchk_stage_merit_split(pid, N, B, xu.ravel(), dz.ravel(), w["xs"].ravel(), w["ref"].ravel(), mu, fext.ravel(), np.float32(w["dt"]), cost7(pm), na, m2.reshape(-1))
         assert n_mismatch(m2, m0) == 0
 
 
