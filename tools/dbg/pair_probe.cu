@@ -1,4 +1,7 @@
-// debug probe: packed pair gradient columns vs scalar columns on the device, per column and per output joint
+// Debug probe (run on a GPU box): the packed-pair gradient columns (rnea_grad_col2_rt) against the scalar columns (rnea_grad_col_rt) ON THE DEVICE, mismatches
+// per column and output joint.  This is the reproducer of the ptxas 12.9 defect described at rbd.cuh: mul2 (mul.rn.f32x2 + add.rn.f32x2 fused into FFMA2);
+// -DGATO_F2_EMULATE=<bits> evaluates fma2 / add2 / mul2 lane by lane to bisect.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -fmad=false --expt-relaxed-constexpr -o tools/dbg/pair_probe tools/dbg/pair_probe.cu
 #include <cstdio>
 #include <vector>
 #include <random>
