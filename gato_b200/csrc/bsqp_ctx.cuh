@@ -37,6 +37,7 @@ constexpr int   kPcgRefThreads = 1024;  // settings.h:25 — fixes the shape of 
 
 struct Ctx {
         int   N, B, it, max_pcg, adapt, flags;
+        int   sms;  // multiprocessors of the device (launch heuristics)
         float dt, thresh;
         Costs cs;
         float*       xu;

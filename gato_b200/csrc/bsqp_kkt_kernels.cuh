@@ -5,53 +5,45 @@
 
 namespace gato {
 
-// =====================================================================================================
-// k_kkt: one thread per work item, three kinds of items in separate warps (blockIdx.y = kind) so that no warp diverges:
-//   kind 0  cost blocks of knot k = 0..N-1 (Q,q,R,r); knot N-1 is the "terminal" item: Q_{N-1}, q_{N-1} evaluated at
-//           x_{N-2} against ref_{N-1} (setup_kkt.cuh:83-100) and c_0 = x_0 - x_s
-//   kind 1  linearised dynamics of knot k = 0..N-2, d/dq half: columns 0..nq-1 of A_k and the defect c_{k+1}
-//   kind 2  d/dqd half: columns nq..nx-1 of A_k and B_k
-// (The two dynamics halves repeat the M^-1 / RNEA prologue; splitting doubles the parallelism of what is a latency-bound
-// kernel at batch 512.)  Results are transposed through shared memory so that HBM/L2 stores are coalesced per knot block.
-// =====================================================================================================
-template<class P>
-__global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
-{
-        constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ, ST = 33;
-        // staged floats per item: kind 0: Q (its nq x nq block and the lower diagonal; everything else in Q is a structural zero) | q |
-        // R (diagonal) | r | c0;  kind 1: half of A | c;  kind 2: half of A | B  -- the largest.  26 KB per warp keeps 8 warps per SM.
-        constexpr int ROWS = NX * NQ + NX * NU;
-        static_assert(ROWS >= NQ * NQ + NQ + NX + NU + NU + NX, "kind 0 fits");
-        if (stopped_before(c, c.it)) return;
-        __shared__ float stage[ROWS * ST];
-        const int        kind = blockIdx.y;
-        const int        lane = threadIdx.x;
-        const int        item0 = blockIdx.x * 32;
-        const int        per = (kind == 0) ? c.N : c.N - 1;  // items per solve
-        const int        total = c.B * per;
-        if (item0 >= total) return;
-        const int  item = item0 + lane;
-        const bool valid = item < total;
-        const int  b = valid ? item / per : 0, k = valid ? item % per : 0;
-        const bool term = (kind == 0) && (k == c.N - 1);
-        const int  traj = (NX + NU) * c.N - NU;
-        const int  ks = term ? k - 1 : k;  // knot whose (x,u) this item evaluates
-        float      xux[2 * NX + NU];
+// What both kernels share: a warp of 32 work items of one kind, one item per lane.  Decodes the items, loads their (x, u, x_next), stages results
+// transposed in shared memory (ROWS rows of 33 floats: row = element, column = lane) and flushes them with (item, element) pairs flattened over
+// the lanes, so that every store instruction is full and consecutive lanes write consecutive addresses; and the cost item (kind 0).
+template<class P, int ROWS>
+struct KktWarp {
+        static constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ, ST = 33;
+        static_assert(ROWS >= NQ * NQ + NQ + NX + NU + NU + NX, "the cost item fits the staging buffer");
+        float* stage;    // [ROWS * ST] shared
+        int*   rowbase;  // [32] shared: global knot index (b * N + k) of the warp's i-th item, bit 30 set for the terminal item (no divisions in the flushes)
+        int    lane, item0, total, b, k, traj;
+        bool   valid, term;
+        float  xux[2 * NX + NU];
+
+        // false: the warp has no item (beyond the grid's last partial block)
+        __device__ __forceinline__ bool init(const Ctx& c, float* stage_, int* rowbase_, bool cost_kind)
         {
+                stage = stage_, rowbase = rowbase_;
+                lane = threadIdx.x, item0 = blockIdx.x * 32;
+                const int per = cost_kind ? c.N : c.N - 1;  // items per solve
+                total = c.B * per;
+                if (item0 >= total) return false;
+                const int item = item0 + lane;
+                valid = item < total;
+                b = valid ? item / per : 0, k = valid ? item % per : 0;
+                term = cost_kind && (k == c.N - 1);
+                traj = (NX + NU) * c.N - NU;
+                const int    ks = term ? k - 1 : k;  // knot whose (x,u) this item evaluates
                 const float* src = c.xu + (size_t)b * traj + (size_t)ks * (NX + NU);
                 sfor<0, 2 * NX + NU>([&](auto ic) { xux[ic] = src[ic]; });
+                rowbase[lane] = (b * c.N + k) | (term ? (1 << 30) : 0);
+                __syncwarp();
+                return true;
         }
-        // write staged rows [row0, row0+count) of every selected item to dst[(b*N + knot + koff)*stride + off + e]
-        // rowbase[i] = global knot index (b * N + k) of the warp's i-th item, bit 30 set for the terminal item: written once, so that the
-        // flushes below need no integer divisions
-        __shared__ int rowbase[32];
-        rowbase[lane] = (b * c.N + k) | (term ? (1 << 30) : 0);
-        __syncwarp();
-        // write staged rows [row0, row0+COUNT) of every selected item to dst[(b*N + knot + koff)*stride + off + e]; the (item, element) pairs are
-        // flattened over the lanes so that every store instruction is full and consecutive lanes write consecutive addresses
-        auto flush = [&](auto count_c, float* dst, int row0, int stride, int off, int koff, int which /*0 non-terminal, 1 terminal, 2 all*/) {
-                constexpr int COUNT = decltype(count_c)::value;
-                const int     nvalid = min(32, total - item0);
+        __device__ __forceinline__ void put(int row, float v) const { stage[row * ST + lane] = v; }
+        // staged rows [row0, row0+COUNT) of every selected item -> dst[(b*N + knot + koff)*stride + off + e]
+        template<int COUNT>
+        __device__ __forceinline__ void flush(float* dst, int row0, int stride, int off, int koff, int which /*0 non-terminal, 1 terminal, 2 all*/) const
+        {
+                const int nvalid = min(32, total - item0);
                 for (int f = lane; f < nvalid * COUNT; f += 32) {
                         const int  i = f / COUNT, e = f - i * COUNT;
                         const int  rb = rowbase[i];
@@ -59,8 +51,11 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
                         if ((which == 0 && ti) || (which == 1 && !ti)) continue;
                         dst[((size_t)(rb & ~(1 << 30)) + koff) * stride + off + e] = stage[(row0 + e) * ST + i];
                 }
-        };
-        if (kind == 0) {
+        }
+        // kind 0: cost blocks of knot k (Q, q, R, r); knot N-1 is the "terminal" item: Q_{N-1}, q_{N-1} evaluated at x_{N-2} against ref_{N-1}
+        // (setup_kkt.cuh:83-100) and c_0 = x_0 - x_s
+        __device__ __forceinline__ void cost_item(const Ctx& c) const
+        {
                 float ref3[3];
                 sfor<0, 3>([&](auto ic) { ref3[ic] = c.ref[(size_t)b * 6 * c.N + 6 * k + ic]; });
                 constexpr int rQ = 0, rQd = NQ * NQ, rq = rQd + NQ, rR = rq + NX, rr = rR + NU, rc0 = rr + NU;
@@ -71,18 +66,18 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
                     [&](int e, float v) {
                             const int i = e / NX, j = e % NX;
                             if (i < NQ && j < NQ)
-                                    stage[(rQ + i * NQ + j) * ST + lane] = v;
+                                    put(rQ + i * NQ + j, v);
                             else if (i == j)
-                                    stage[(rQd + i - NQ) * ST + lane] = v;
+                                    put(rQd + i - NQ, v);
                     },
-                    [&](int e, float v) { stage[(rq + e) * ST + lane] = v; },
+                    [&](int e, float v) { put(rq + e, v); },
                     [&](int e, float v) {
-                            if (e / NU == e % NU) stage[(rR + e / NU) * ST + lane] = v;
+                            if (e / NU == e % NU) put(rR + e / NU, v);
                     },
-                    [&](int e, float v) { stage[(rr + e) * ST + lane] = v; }, term, term || Items<P>::pos_form_b_for(c.N));
+                    [&](int e, float v) { put(rr + e, v); }, term, term || Items<P>::pos_form_b_for(c.N));
                 if (term && valid) {
                         const float* x0 = c.xu + (size_t)b * traj;
-                        sfor<0, NX>([&](auto ic) { stage[(rc0 + ic) * ST + lane] = x0[ic] - c.xs[(size_t)b * NX + ic]; });
+                        sfor<0, NX>([&](auto ic) { put(rc0 + ic, x0[ic] - c.xs[(size_t)b * NX + ic]); });
                 }
                 __syncwarp();
                 {  // Q and R: expand the staged entries, zeros elsewhere ((item, element) pairs flattened over the lanes like flush)
@@ -103,26 +98,52 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
                                 c.R[(size_t)rb * NU * NU + e] = (r_ == c_) ? stage[(rR + r_) * ST + i] : 0.0f;
                         }
                 }
-                flush(std::integral_constant<int, NX>{}, c.q, rq, NX, 0, 0, 2);
-                flush(std::integral_constant<int, NU>{}, c.r, rr, NU, 0, 0, 0);
-                flush(std::integral_constant<int, NX>{}, c.c, rc0, NX, 0, -(c.N - 1), 1);
+                flush<NX>(c.q, rq, NX, 0, 0, 2);
+                flush<NU>(c.r, rr, NU, 0, 0, 0);
+                flush<NX>(c.c, rc0, NX, 0, -(c.N - 1), 1);
+        }
+};
+
+// =====================================================================================================
+// k_kkt: one thread per work item, three kinds of items in separate warps (blockIdx.y = kind) so that no warp diverges:
+//   kind 0  cost blocks of knot k = 0..N-1 (KktWarp::cost_item)
+//   kind 1  linearised dynamics of knot k = 0..N-2, d/dq half: columns 0..nq-1 of A_k and the defect c_{k+1}
+//   kind 2  d/dqd half: columns nq..nx-1 of A_k and B_k
+// (The two dynamics halves repeat the M^-1 / RNEA prologue; splitting doubles the parallelism of what is a latency-bound
+// kernel at batch 512.)  Results are transposed through shared memory so that HBM/L2 stores are coalesced per knot block.
+// =====================================================================================================
+template<class P>
+__global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
+{
+        constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ;
+        // staged floats per item: kind 0: Q (its nq x nq block and the lower diagonal; everything else in Q is a structural zero) | q |
+        // R (diagonal) | r | c0;  kind 1: half of A | c;  kind 2: half of A | B  -- the largest.  26 KB per warp keeps 8 warps per SM.
+        constexpr int ROWS = NX * NQ + NX * NU;
+        if (stopped_before(c, c.it)) return;
+        __shared__ float stage[ROWS * KktWarp<P, ROWS>::ST];
+        __shared__ int   rowbase[32];
+        const int        kind = blockIdx.y;
+        KktWarp<P, ROWS> w;
+        if (!w.init(c, stage, rowbase, kind == 0)) return;
+        if (kind == 0) {
+                w.cost_item(c);
+                return;
+        }
+        float fext[6];
+        sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * w.b + ic]; });
+        constexpr int rA = 0, rX = NX * NQ;  // half of A (NX*NQ contiguous floats), then c (kind 1) or B (kind 2)
+        if (kind == 1) {
+                Items<P>::template linearize_half_rolled<0>(
+                    w.xux, fext, c.dt, [&](int e, float v) { w.put(rA + e, v); }, [&](int, float) {}, [&](int e, float v) { w.put(rX + e, v); });
+                __syncwarp();
+                w.template flush<NX * NQ>(c.A, rA, NX * NX, 0, 0, 2);
+                w.template flush<NX>(c.c, rX, NX, 0, 1, 2);
         } else {
-                float fext[6];
-                sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * b + ic]; });
-                constexpr int rA = 0, rX = NX * NQ;  // half of A (NX*NQ contiguous floats), then c (kind 1) or B (kind 2)
-                if (kind == 1) {
-                        Items<P>::template linearize_half_rolled<0>(
-                            xux, fext, c.dt, [&](int e, float v) { stage[(rA + e) * ST + lane] = v; }, [&](int, float) {}, [&](int e, float v) { stage[(rX + e) * ST + lane] = v; });
-                        __syncwarp();
-                        flush(std::integral_constant<int, NX * NQ>{}, c.A, rA, NX * NX, 0, 0, 2);
-                        flush(std::integral_constant<int, NX>{}, c.c, rX, NX, 0, 1, 2);
-                } else {
-                        Items<P>::template linearize_half_rolled<1>(
-                            xux, fext, c.dt, [&](int e, float v) { stage[(rA + e - NX * NQ) * ST + lane] = v; }, [&](int e, float v) { stage[(rX + e) * ST + lane] = v; }, [&](int, float) {});
-                        __syncwarp();
-                        flush(std::integral_constant<int, NX * NQ>{}, c.A, rA, NX * NX, NX * NQ, 0, 2);
-                        flush(std::integral_constant<int, NX * NU>{}, c.Bm, rX, NX * NU, 0, 0, 2);
-                }
+                Items<P>::template linearize_half_rolled<1>(
+                    w.xux, fext, c.dt, [&](int e, float v) { w.put(rA + e - NX * NQ, v); }, [&](int e, float v) { w.put(rX + e, v); }, [&](int, float) {});
+                __syncwarp();
+                w.template flush<NX * NQ>(c.A, rA, NX * NX, NX * NQ, 0, 2);
+                w.template flush<NX * NU>(c.Bm, rX, NX * NU, 0, 0, 2);
         }
 }
 
@@ -136,111 +157,37 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
 template<class P>
 __global__ void __launch_bounds__(32) k_kkt_fine(Ctx c)
 {
-        constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ, ST = 33;
+        constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ;
         constexpr int ROWS = NX * NU + NX;  // kind 1 stages the most: B | c
-        static_assert(ROWS >= NQ * NQ + NQ + NX + NU + NU + NX, "kind 0 fits");
         if (stopped_before(c, c.it)) return;
-        __shared__ float stage[ROWS * ST];
+        __shared__ float stage[ROWS * KktWarp<P, ROWS>::ST];
+        __shared__ int   rowbase[32];
         const int        kind = blockIdx.y;
-        const int        lane = threadIdx.x;
-        const int        item0 = blockIdx.x * 32;
-        const int        per = (kind == 0) ? c.N : c.N - 1;
-        const int        total = c.B * per;
-        if (item0 >= total) return;
-        const int  item = item0 + lane;
-        const bool valid = item < total;
-        const int  b = valid ? item / per : 0, k = valid ? item % per : 0;
-        const bool term = (kind == 0) && (k == c.N - 1);
-        const int  traj = (NX + NU) * c.N - NU;
-        const int  ks = term ? k - 1 : k;
-        float      xux[2 * NX + NU];
-        {
-                const float* src = c.xu + (size_t)b * traj + (size_t)ks * (NX + NU);
-                sfor<0, 2 * NX + NU>([&](auto ic) { xux[ic] = src[ic]; });
-        }
-        // rowbase[i] = global knot index (b * N + k) of the warp's i-th item, bit 30 set for the terminal item: written once, so that the
-        // flushes below need no integer divisions
-        __shared__ int rowbase[32];
-        rowbase[lane] = (b * c.N + k) | (term ? (1 << 30) : 0);
-        __syncwarp();
-        // write staged rows [row0, row0+COUNT) of every selected item to dst[(b*N + knot + koff)*stride + off + e]; the (item, element) pairs are
-        // flattened over the lanes so that every store instruction is full and consecutive lanes write consecutive addresses
-        auto flush = [&](auto count_c, float* dst, int row0, int stride, int off, int koff, int which /*0 non-terminal, 1 terminal, 2 all*/) {
-                constexpr int COUNT = decltype(count_c)::value;
-                const int     nvalid = min(32, total - item0);
-                for (int f = lane; f < nvalid * COUNT; f += 32) {
-                        const int  i = f / COUNT, e = f - i * COUNT;
-                        const int  rb = rowbase[i];
-                        const bool ti = (rb >> 30) & 1;
-                        if ((which == 0 && ti) || (which == 1 && !ti)) continue;
-                        dst[((size_t)(rb & ~(1 << 30)) + koff) * stride + off + e] = stage[(row0 + e) * ST + i];
-                }
-        };
+        KktWarp<P, ROWS> w;
+        if (!w.init(c, stage, rowbase, kind == 0)) return;
         if (kind == 0) {
-                float ref3[3];
-                sfor<0, 3>([&](auto ic) { ref3[ic] = c.ref[(size_t)b * 6 * c.N + 6 * k + ic]; });
-                constexpr int rQ = 0, rQd = NQ * NQ, rq = rQd + NQ, rR = rq + NX, rr = rR + NU, rc0 = rr + NU;
-                Items<P>::template cost_grad_hess<true>(
-                    xux, ref3, c.cs,
-                    [&](int e, float v) {
-                            const int i = e / NX, j = e % NX;
-                            if (i < NQ && j < NQ)
-                                    stage[(rQ + i * NQ + j) * ST + lane] = v;
-                            else if (i == j)
-                                    stage[(rQd + i - NQ) * ST + lane] = v;
-                    },
-                    [&](int e, float v) { stage[(rq + e) * ST + lane] = v; },
-                    [&](int e, float v) {
-                            if (e / NU == e % NU) stage[(rR + e / NU) * ST + lane] = v;
-                    },
-                    [&](int e, float v) { stage[(rr + e) * ST + lane] = v; }, term, term || Items<P>::pos_form_b_for(c.N));
-                if (term && valid) {
-                        const float* x0 = c.xu + (size_t)b * traj;
-                        sfor<0, NX>([&](auto ic) { stage[(rc0 + ic) * ST + lane] = x0[ic] - c.xs[(size_t)b * NX + ic]; });
-                }
-                __syncwarp();
-                {  // Q and R: expand the staged entries, zeros elsewhere ((item, element) pairs flattened over the lanes like flush)
-                        const int nvalid = min(32, total - item0);
-                        for (int f = lane; f < nvalid * NX * NX; f += 32) {
-                                const int i = f / (NX * NX), e = f - i * (NX * NX), r_ = e / NX, c_ = e - r_ * NX;
-                                float     v = 0.0f;
-                                if (r_ < NQ && c_ < NQ)
-                                        v = stage[(rQ + r_ * NQ + c_) * ST + i];
-                                else if (r_ == c_)
-                                        v = stage[(rQd + r_ - NQ) * ST + i];
-                                c.Q[(size_t)(rowbase[i] & ~(1 << 30)) * NX * NX + e] = v;
-                        }
-                        for (int f = lane; f < nvalid * NU * NU; f += 32) {
-                                const int i = f / (NU * NU), e = f - i * (NU * NU), r_ = e / NU, c_ = e - r_ * NU;
-                                const int rb = rowbase[i];
-                                if ((rb >> 30) & 1) continue;  // the terminal item has no R
-                                c.R[(size_t)rb * NU * NU + e] = (r_ == c_) ? stage[(rR + r_) * ST + i] : 0.0f;
-                        }
-                }
-                flush(std::integral_constant<int, NX>{}, c.q, rq, NX, 0, 0, 2);
-                flush(std::integral_constant<int, NU>{}, c.r, rr, NU, 0, 0, 0);
-                flush(std::integral_constant<int, NX>{}, c.c, rc0, NX, 0, -(c.N - 1), 1);
+                w.cost_item(c);
                 return;
         }
         float fext[6];
-        sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * b + ic]; });
+        sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * w.b + ic]; });
         typename Rbd<P>::DynState st;
-        Rbd<P>::dyn_prologue(xux, xux + NQ, xux + NX, fext, st);
+        Rbd<P>::dyn_prologue(w.xux, w.xux + NQ, w.xux + NX, fext, st);
         if (kind == 1) {
                 constexpr int rB = 0, rc = NX * NU;
-                Items<P>::linearize_base(st, xux, c.dt, [&](int e, float v) { stage[(rB + e) * ST + lane] = v; }, [&](int e, float v) { stage[(rc + e) * ST + lane] = v; });
+                Items<P>::linearize_base(st, w.xux, c.dt, [&](int e, float v) { w.put(rB + e, v); }, [&](int e, float v) { w.put(rc + e, v); });
                 __syncwarp();
-                flush(std::integral_constant<int, NX * NU>{}, c.Bm, rB, NX * NU, 0, 0, 2);
-                flush(std::integral_constant<int, NX>{}, c.c, rc, NX, 0, 1, 2);
+                w.template flush<NX * NU>(c.Bm, rB, NX * NU, 0, 0, 2);
+                w.template flush<NX>(c.c, rc, NX, 0, 1, 2);
                 return;
         }
         const int col = kind - 2;  // column of A
         sfor<0, NX>([&](auto cc) {
                 constexpr int cidx = cc;
-                if (col == cidx) Items<P>::template linearize_column<cidx / NQ, cidx % NQ>(st, xux + NQ, c.dt, [&](int e, float v) { stage[(e - cidx * NX) * ST + lane] = v; });
+                if (col == cidx) Items<P>::template linearize_column<cidx / NQ, cidx % NQ>(st, w.xux + NQ, c.dt, [&](int e, float v) { w.put(e - cidx * NX, v); });
         });
         __syncwarp();
-        flush(std::integral_constant<int, NX>{}, c.A, 0, NX * NX, col * NX, 0, 2);
+        w.template flush<NX>(c.A, 0, NX * NX, col * NX, 0, 2);
 }
 
 }  // namespace gato

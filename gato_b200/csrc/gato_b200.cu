@@ -110,6 +110,7 @@ struct gato_solver {
         };
         std::vector<GraphEntry> graphs;
         bool                    use_graph = false;
+        int                     sms = 148;  // multiprocessors of the device
         DevArr<unsigned> num_solved, num_unsolved, pcg_done;
         bool             overlap = true;  // merit / line search overlapped with the tail of k_pcg (GATO_NO_OVERLAP=1 switches it off)
         DevArr<float>    st_xu, st_xs, st_ref, st_xkp1, st_xk, st_uk;  // staging for *_host calls
@@ -175,6 +176,7 @@ int configure_kernels(gato_solver* s)
 Ctx make_ctx(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref, float dt)
 {
         Ctx c{};
+        c.sms = s->sms;
         c.N = s->N, c.B = s->B, c.it = 0, c.max_pcg = (int)s->prm.max_pcg_iters, c.adapt = s->adapt_rho ? 1 : 0, c.flags = 0;
         c.dt = dt;
         c.thresh = (float)(uint32_t)s->B * s->prm.solve_ratio;
@@ -479,6 +481,10 @@ int gato_create(gato_solver** out, int plant, int N, int B, int device, void* st
                 }
                 s->own_stream = true;
         }
+        if (cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || s->sms < 1) {
+                s->err = "cudaDeviceGetAttribute(multiProcessorCount) failed";
+                return fail(GATO_ERR_CUDA);
+        }
         int rc = plant == GATO_PLANT_IIWA14 ? configure_kernels<Iiwa14>(s) : configure_kernels<Indy7>(s);
         if (rc) return fail(rc);
         const Dims&  d = s->d;
@@ -512,7 +518,7 @@ int gato_create(gato_solver** out, int plant, int N, int B, int device, void* st
         s->h_sqp_iters.assign(B, 0);
         s->overlap = !getenv("GATO_NO_OVERLAP");
         // graphs for the regime where the launches, not the kernels, set the latency (the split line-search kernel's regime: no overlapped launch inside)
-        s->use_graph = B <= 148 && !getenv("GATO_NO_GRAPH");
+        s->use_graph = B <= s->sms && !getenv("GATO_NO_GRAPH");
         // per-batch hyper-parameters  (bsqp.cuh:48-58)
         std::vector<float> rho0(B, prm->rho), drho0(B, 1.0f), mu(B, prm->mu), tol(B, prm->pcg_tol);
         cudaMemcpy(s->rho.p, rho0.data(), sizeof(float) * B, cudaMemcpyHostToDevice);

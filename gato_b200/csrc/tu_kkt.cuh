@@ -9,8 +9,8 @@ void enqueue_kkt<GATO_TU_PLANT>(const Ctx& c, cudaStream_t st)
         const int warps = (items + 31) / 32;
         constexpr int kFineKinds = 2 + 4 * GATO_TU_PLANT::NQ / 2;  // 2 + 2 nq
         // small grids (the MPC regime): one column of the linearisation per thread, as long as all its warps are resident at once
-        // (148 SMs x 8 warps of 255 registers)
-        if (warps * kFineKinds <= 148 * 8)
+        // (8 warps of 255 registers per SM)
+        if (warps * kFineKinds <= c.sms * 8)
                 k_kkt_fine<GATO_TU_PLANT><<<dim3(warps, kFineKinds), 32, 0, st>>>(c);
         else
                 k_kkt<GATO_TU_PLANT><<<dim3(warps, 3), 32, 0, st>>>(c);

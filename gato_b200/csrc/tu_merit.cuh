@@ -16,7 +16,7 @@ bool enqueue_merit<GATO_TU_PLANT>(const Ctx& c, int na, cudaStream_t st)
 {
         const size_t smem = sizeof(float) * (size_t)(na * c.N + na);
         // small batches (one CTA per SM at most) with room for two threads per (alpha, knot) in one block: the split kernel
-        if (na == kNumAlphas && c.B <= 148 && 2 * na * c.N <= 512) {
+        if (na == kNumAlphas && c.B <= c.sms && 2 * na * c.N <= 512) {
                 const int threads = (2 * na * c.N + 31) / 32 * 32;
                 Ctx       k = c;
                 k.flags &= ~F_OVERLAP;
