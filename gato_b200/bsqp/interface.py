@@ -11,6 +11,10 @@ class BSQP:
     def __init__(self, model_path, batch_size, N, dt, max_sqp_iters=10, kkt_tol=1e-4, max_pcg_iters=100, pcg_tol=1e-4, solve_ratio=1.0, mu=1.0, q_cost=2.0, qd_cost=1e-4,
                  u_cost=1e-6, N_cost=50.0, q_lim_cost=1e-3, vel_lim_cost=0.0, ctrl_lim_cost=0.0, rho=0.0, rho_batch=None, mu_batch=None, pcg_tol_batch=None, adapt_rho=True,
                  plant_type="indy7"):
+        if model_path and str(model_path).endswith(".gmdl"):
+            # a robot given as a data file (gato_model_load / gato_model_register): its solves run the table-driven kernels.  (The reference takes
+            # a URDF here, for pinocchio only -- its solver is compiled per robot.)
+            plant_type = native.Model.load(model_path).register()
         if plant_type is None:  # interface.py:37-41
             plant_type = "iiwa14" if (model_path and "iiwa" in str(model_path).lower()) else "indy7"
         try:

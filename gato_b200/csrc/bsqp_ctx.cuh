@@ -38,6 +38,7 @@ constexpr int   kPcgRefThreads = 1024;  // settings.h:25 — fixes the shape of 
 struct Ctx {
         int   N, B, it, max_pcg, adapt, flags;
         int   sms;  // multiprocessors of the device (launch heuristics)
+        int   model_slot;  // run-time models: constant-memory slot of the robot's tables (rt_slots.cuh); unused by the compiled plants
         float dt, thresh;
         Costs cs;
         float*       xu;

@@ -2,6 +2,7 @@
 #pragma once
 #include "bsqp_ctx.cuh"
 #include "items.cuh"
+#include "rt_slots.cuh"
 
 namespace gato {
 
@@ -61,7 +62,8 @@ struct KktWarp {
                 constexpr int rQ = 0, rQd = NQ * NQ, rq = rQd + NQ, rR = rq + NX, rr = rR + NU, rc0 = rr + NU;
                 // Q = [[h h^T w + barrier terms, 0], [0, diag]], R = diag (plant cost Hessians, iiwa14_plant.cuh:400-450): only those entries
                 // are staged; the indices are compile-time constants after inlining, so the stores of structural zeros fold away
-                Items<P>::template cost_grad_hess<true>(
+                const Items<P> it = make_items<P>(c);
+                it.template cost_grad_hess<true>(
                     xux, ref3, c.cs,
                     [&](int e, float v) {
                             const int i = e / NX, j = e % NX;
@@ -132,14 +134,15 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
         float fext[6];
         sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * w.b + ic]; });
         constexpr int rA = 0, rX = NX * NQ;  // half of A (NX*NQ contiguous floats), then c (kind 1) or B (kind 2)
+        const Items<P> it = make_items<P>(c);
         if (kind == 1) {
-                Items<P>::template linearize_half_rolled<0>(
+                it.template linearize_half_rolled<0>(
                     w.xux, fext, c.dt, [&](int e, float v) { w.put(rA + e, v); }, [&](int, float) {}, [&](int e, float v) { w.put(rX + e, v); });
                 __syncwarp();
                 w.template flush<NX * NQ>(c.A, rA, NX * NX, 0, 0, 2);
                 w.template flush<NX>(c.c, rX, NX, 0, 1, 2);
         } else {
-                Items<P>::template linearize_half_rolled<1>(
+                it.template linearize_half_rolled<1>(
                     w.xux, fext, c.dt, [&](int e, float v) { w.put(rA + e - NX * NQ, v); }, [&](int e, float v) { w.put(rX + e, v); }, [&](int, float) {});
                 __syncwarp();
                 w.template flush<NX * NQ>(c.A, rA, NX * NX, NX * NQ, 0, 2);
@@ -171,21 +174,19 @@ __global__ void __launch_bounds__(32) k_kkt_fine(Ctx c)
         }
         float fext[6];
         sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * w.b + ic]; });
-        typename Rbd<P>::DynState st;
-        Rbd<P>::dyn_prologue(w.xux, w.xux + NQ, w.xux + NX, fext, st);
+        const Items<P>              it = make_items<P>(c);
+        typename Items<P>::DynState st;
+        it.prologue(w.xux, fext, st);
         if (kind == 1) {
                 constexpr int rB = 0, rc = NX * NU;
-                Items<P>::linearize_base(st, w.xux, c.dt, [&](int e, float v) { w.put(rB + e, v); }, [&](int e, float v) { w.put(rc + e, v); });
+                it.linearize_base(st, w.xux, c.dt, [&](int e, float v) { w.put(rB + e, v); }, [&](int e, float v) { w.put(rc + e, v); });
                 __syncwarp();
                 w.template flush<NX * NU>(c.Bm, rB, NX * NU, 0, 0, 2);
                 w.template flush<NX>(c.c, rc, NX, 0, 1, 2);
                 return;
         }
         const int col = kind - 2;  // column of A
-        sfor<0, NX>([&](auto cc) {
-                constexpr int cidx = cc;
-                if (col == cidx) Items<P>::template linearize_column<cidx / NQ, cidx % NQ>(st, w.xux + NQ, c.dt, [&](int e, float v) { w.put(e - cidx * NX, v); });
-        });
+        it.linearize_column_any(col, st, w.xux + NQ, c.dt, [&](int e, float v) { w.put(e - col * NX, v); });
         __syncwarp();
         w.template flush<NX>(c.A, 0, NX * NX, col * NX, 0, 2);
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include "bsqp_ctx.cuh"
 #include "items.cuh"
+#include "rt_slots.cuh"
 
 namespace gato {
 
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(SPLIT ? 512 : (NA == 1 ? 128 : 256), (NA == 1 
                 const bool  zero_dz = (c.flags & F_ZERO_DZ) != 0;
                 float       fext[6];
                 sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * b + ic]; });
+                const Items<P> it = make_items<P>(c);
                 for (int w0 = tid; w0 < (SPLIT ? 2 : 1) * NA * N; w0 += T) {
                         const int   half = SPLIT ? w0 / (NA * N) : 0, w = SPLIT ? w0 % (NA * N) : w0;
                         const int   a = w / N, k = w % N;
@@ -52,9 +54,9 @@ __global__ void __launch_bounds__(SPLIT ? 512 : (NA == 1 ? 128 : 256), (NA == 1 
                                 else
                                         sfor<0, 2 * NX + NU>([&](auto ic) { xux[ic] = fmaf(alpha, dk[ic], xk[ic]); });
                                 if constexpr (SPLIT)
-                                        m = half == 0 ? Items<P>::merit_mid_cons(xux, fext, c.dt) : Items<P>::template tracking_cost<false>(xux, ref3, c.cs);
+                                        m = half == 0 ? it.merit_mid_cons(xux, fext, c.dt) : it.template tracking_cost<false>(xux, ref3, c.cs);
                                 else
-                                        m = Items<P>::merit_mid(xux, ref3, mu, fext, c.dt, c.cs);
+                                        m = it.merit_mid(xux, ref3, mu, fext, c.dt, c.cs);
                         } else {
                                 float e0[NX];
                                 if (zero_dz) {
@@ -65,9 +67,9 @@ __global__ void __launch_bounds__(SPLIT ? 512 : (NA == 1 ? 128 : 256), (NA == 1 
                                         sfor<0, NX>([&](auto ic) { e0[ic] = fabsf(fmaf(alpha, dz[ic], xu[ic]) - c.xs[(size_t)b * NX + ic]); });
                                 }
                                 if constexpr (SPLIT)
-                                        m = half == 0 ? Items<P>::merit_last_cons(e0) : Items<P>::template tracking_cost<true>(xux, ref3, c.cs);
+                                        m = half == 0 ? it.merit_last_cons(e0) : it.template tracking_cost<true>(xux, ref3, c.cs);
                                 else
-                                        m = Items<P>::merit_last(xux, ref3, mu, e0, c.cs);
+                                        m = it.merit_last(xux, ref3, mu, e0, c.cs);
                         }
                         if (SPLIT && half == 1)
                                 mcost[a * N + k] = m;
@@ -171,17 +173,16 @@ __global__ void __launch_bounds__(SPLIT ? 512 : (NA == 1 ? 128 : 256), (NA == 1 
 // k_sim_forward: thread per solve — simForwardBatchedKernel / sim_step (sim.cuh:16-49, integrator.cuh:191-209)
 // =====================================================================================================
 template<class P>
-__global__ void __launch_bounds__(64) k_sim_forward(int B, float* xkp1, const float* xk, const float* uk, const float* fext, float dt)
+__global__ void __launch_bounds__(64) k_sim_forward(int B, float* xkp1, const float* xk, const float* uk, const float* fext, float dt, int model_slot)
 {
         constexpr int NQ = P::NQ, NX = 2 * NQ;
         const int     b = blockIdx.x * blockDim.x + threadIdx.x;
         if (b >= B) return;
-        float x[NX], u[NQ], fe[6], qdd[NQ], qn[NQ], qdn[NQ];
+        float x[NX], u[NQ], fe[6], qn[NQ], qdn[NQ];
         sfor<0, NX>([&](auto ic) { x[ic] = xk[ic]; });
         sfor<0, NQ>([&](auto ic) { u[ic] = uk[ic]; });
         sfor<0, 6>([&](auto ic) { fe[ic] = fext[6 * b + ic]; });
-        Rbd<P>::forward_dynamics(x, x + NQ, u, fe, qdd);
-        Rbd<P>::integrate(x, x + NQ, qdd, dt, qn, qdn);
+        make_items_slot<P>(model_slot).sim_step(x, u, fe, dt, qn, qdn);
         sfor<0, NQ>([&](auto ic) {
                 xkp1[(size_t)b * NX + ic] = qn[ic];
                 xkp1[(size_t)b * NX + NQ + ic] = qdn[ic];
@@ -193,14 +194,14 @@ __global__ void __launch_bounds__(64) k_sim_forward(int B, float* xkp1, const fl
 // the Python wrapper's ee_pos (python/bsqp/interface.py:212-214, which calls pinocchio there)
 // =====================================================================================================
 template<class P>
-__global__ void __launch_bounds__(64) k_ee_pos(int n, const float* q, float* ee)
+__global__ void __launch_bounds__(64) k_ee_pos(int n, const float* q, float* ee, int model_slot)
 {
         constexpr int NQ = P::NQ;
         const int     i = blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= n) return;
         float qi[NQ], e[3];
         sfor<0, NQ>([&](auto ic) { qi[ic] = q[(size_t)i * NQ + ic]; });
-        Rbd<P>::ee_pos(qi, e);
+        make_items_slot<P>(model_slot).ee_pos(qi, e);
         sfor<0, 3>([&](auto ic) { ee[(size_t)i * 3 + ic] = e[ic]; });
 }
 

@@ -56,10 +56,39 @@ struct DevArr {
         }
 };
 
+// ---- run-time robot models (include/gato_b200.h: gato_model_*) ------------------------------------------------------------------
+// Registered models live for the life of the process; plant id = GATO_PLANT_MODEL0 + index = constant-memory slot + GATO_PLANT_MODEL0.
+struct RegisteredModel {
+        gato_model desc;
+        RtModel    rt;
+};
+std::mutex                   g_model_mu;
+std::vector<RegisteredModel> g_models;
+
+// joints of a plant id, or 0 if the id names neither a compiled plant nor a registered model
+int plant_nq(int plant)
+{
+        if (plant == GATO_PLANT_INDY7) return 6;
+        if (plant == GATO_PLANT_IIWA14) return 7;
+        std::lock_guard<std::mutex> lk(g_model_mu);
+        const int                   i = plant - GATO_PLANT_MODEL0;
+        return (i >= 0 && i < (int)g_models.size()) ? g_models[i].rt.nq : 0;
+}
+// f(plant tag): the compiled plants and the table-driven instantiations for nq = 6 / 7
+template<class F>
+auto with_plant(int plant, int nq, F&& f)
+{
+        if (plant == GATO_PLANT_INDY7) return f(Indy7{});
+        if (plant == GATO_PLANT_IIWA14) return f(Iiwa14{});
+        if (nq == 6) return f(RtPlant<6>{});
+        return f(RtPlant<7>{});
+}
+
 }  // namespace
 
 struct gato_solver {
         int          plant, N, B, device;
+        int          model_slot = 0;  // run-time models: plant - GATO_PLANT_MODEL0
         Dims         d;
         gato_params  prm;
         bool         adapt_rho = true;
@@ -127,7 +156,10 @@ struct gato_solver {
         int                                            pcg_threads = 0, pcg_rpt = 0;
         bool                                           pcg_cluster = false;  // long horizons: thread-block cluster per solve (k_pcg_cluster) instead of streaming
 
-        gato_solver(int plant_, int N_, int B_, int dev) : plant(plant_), N(N_), B(B_), device(dev), d(plant_ ? 7 : 6, N_), prm{}, max_it(1), n_it(1) {}
+        gato_solver(int plant_, int nq_, int N_, int B_, int dev)
+            : plant(plant_), N(N_), B(B_), device(dev), model_slot(plant_ >= GATO_PLANT_MODEL0 ? plant_ - GATO_PLANT_MODEL0 : 0), d(nq_, N_), prm{}, max_it(1), n_it(1)
+        {
+        }
 };
 
 namespace {
@@ -177,6 +209,7 @@ Ctx make_ctx(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref,
 {
         Ctx c{};
         c.sms = s->sms;
+        c.model_slot = s->model_slot;
         c.N = s->N, c.B = s->B, c.it = 0, c.max_pcg = (int)s->prm.max_pcg_iters, c.adapt = s->adapt_rho ? 1 : 0, c.flags = 0;
         c.dt = dt;
         c.thresh = (float)(uint32_t)s->B * s->prm.solve_ratio;
@@ -311,7 +344,7 @@ int enqueue_solve(gato_solver* s, float* d_xu, const float* d_xs, const float* d
 
 int enqueue_direct(gato_solver* s, float* d_xu, const float* d_xs, const float* d_ref, float dt)
 {
-        return s->plant == GATO_PLANT_IIWA14 ? enqueue_solve<Iiwa14>(s, d_xu, d_xs, d_ref, dt) : enqueue_solve<Indy7>(s, d_xu, d_xs, d_ref, dt);
+        return with_plant(s->plant, s->d.nq, [&](auto P) { return enqueue_solve<decltype(P)>(s, d_xu, d_xs, d_ref, dt); });
 }
 
 // Small batches: the same sequence (memsets, 4 * iterations + 1 kernels, the side-stream fork / join, the copies of the statistics to pinned
@@ -392,8 +425,9 @@ extern "C" {
 
 int gato_dims(int plant, int N, int* nx, int* nu, int* traj)
 {
-        if ((plant != 0 && plant != 1) || N < 3) return GATO_ERR_ARG;
-        Dims d(plant ? 7 : 6, N);
+        const int nq = plant_nq(plant);
+        if (!nq || N < 3) return GATO_ERR_ARG;
+        Dims d(nq, N);
         if (nx) *nx = d.nx;
         if (nu) *nu = d.nu;
         if (traj) *traj = d.traj;
@@ -450,13 +484,184 @@ int gato_get_kernel_times(gato_solver* s, float* total_ms, int* launches)
         return GATO_OK;
 }
 
+
+// ---- run-time robot models --------------------------------------------------------------------------------------------------
+extern "C++" {
+namespace {
+template<class P>
+void fill_builtin(gato_model* m, const char* name, int style)
+{
+        memset(m, 0, sizeof(*m));
+        snprintf(m->name, sizeof(m->name), "%s", name);
+        constexpr int nq = P::NQ;
+        m->nq = nq, m->style = style;
+        for (int i = 0; i < 36 * nq; i++) m->X[i] = P::TABLE[i], m->I[i] = P::TABLE[36 * nq + i];
+        for (int i = 0; i < 16 * nq; i++) m->Xhom[i] = P::TABLE[72 * nq + i], m->dXhom[i] = P::TABLE[72 * nq + 16 * nq + i];
+        for (int j = 0; j < nq; j++) m->joint_limit[j] = P::JL[j], m->vel_limit[j] = P::VL[j], m->ctrl_limit[j] = P::CL[j];
+        m->n_x_trig = P::NXT, m->n_xh_trig = P::NXHT, m->n_dxh_trig = P::NDXHT;
+        for (int i = 0; i < P::NXT; i++) m->x_trig[i] = gato_trig{P::XT[i].idx, P::XT[i].k, P::XT[i].coef};
+        for (int i = 0; i < P::NXHT; i++) m->xh_trig[i] = gato_trig{P::XHT[i].idx, P::XHT[i].k, P::XHT[i].coef};
+        for (int i = 0; i < P::NDXHT; i++) m->dxh_trig[i] = gato_trig{P::DXHT[i].idx, P::DXHT[i].k, P::DXHT[i].coef};
+}
+}  // namespace
+}  // extern "C++"
+
+int gato_model_builtin(int plant, gato_model* out)
+{
+        if (!out) return GATO_ERR_ARG;
+        if (plant == GATO_PLANT_IIWA14)
+                fill_builtin<Iiwa14>(out, "iiwa14", 1);
+        else if (plant == GATO_PLANT_INDY7)
+                fill_builtin<Indy7>(out, "indy7", 0);
+        else
+                return GATO_ERR_ARG;
+        return GATO_OK;
+}
+
+// Text format: "gato_model 1", then `key values...` records; numbers with 17 significant digits so that a save / load round trip is exact.
+int gato_model_save(const gato_model* m, const char* path)
+{
+        if (!m || !path || m->nq < 1 || m->nq > GATO_MODEL_MAX_NQ) return GATO_ERR_ARG;
+        FILE* f = fopen(path, "w");
+        if (!f) {
+                g_create_error = std::string("cannot write ") + path;
+                return GATO_ERR_ARG;
+        }
+        const int nq = m->nq;
+        fprintf(f, "gato_model 1\nname %s\nnq %d\nstyle %d\n", m->name[0] ? m->name : "robot", nq, m->style);
+        auto vec = [&](const char* key, const double* v, int n) {
+                fprintf(f, "%s", key);
+                for (int i = 0; i < n; i++) fprintf(f, " %.17g", v[i]);
+                fprintf(f, "\n");
+        };
+        vec("joint_limit", m->joint_limit, nq), vec("vel_limit", m->vel_limit, nq), vec("ctrl_limit", m->ctrl_limit, nq);
+        for (int j = 0; j < nq; j++) {
+                char key[32];
+                snprintf(key, sizeof(key), "X %d", j), vec(key, m->X + 36 * j, 36);
+                snprintf(key, sizeof(key), "I %d", j), vec(key, m->I + 36 * j, 36);
+                snprintf(key, sizeof(key), "Xhom %d", j), vec(key, m->Xhom + 16 * j, 16);
+                snprintf(key, sizeof(key), "dXhom %d", j), vec(key, m->dXhom + 16 * j, 16);
+        }
+        auto trig = [&](const char* key, const gato_trig* t, int n) {
+                fprintf(f, "%s %d\n", key, n);
+                for (int i = 0; i < n; i++) fprintf(f, "%d %.17g %d\n", t[i].idx, t[i].coef, t[i].k);
+        };
+        trig("x_trig", m->x_trig, m->n_x_trig), trig("xh_trig", m->xh_trig, m->n_xh_trig), trig("dxh_trig", m->dxh_trig, m->n_dxh_trig);
+        fprintf(f, "end\n");
+        const bool ok = !ferror(f);
+        fclose(f);
+        return ok ? GATO_OK : GATO_ERR_ARG;
+}
+
+int gato_model_load(const char* path, gato_model* out)
+{
+        if (!path || !out) return GATO_ERR_ARG;
+        FILE* f = fopen(path, "r");
+        if (!f) {
+                g_create_error = std::string("cannot read ") + path;
+                return GATO_ERR_ARG;
+        }
+        memset(out, 0, sizeof(*out));
+        auto bad = [&](const std::string& why) {
+                g_create_error = std::string(path) + ": " + why;
+                fclose(f);
+                return GATO_ERR_ARG;
+        };
+        char key[64];
+        int  version = 0;
+        if (fscanf(f, "%63s %d", key, &version) != 2 || strcmp(key, "gato_model") != 0 || version != 1) return bad("not a gato_model version 1 file");
+        bool ended = false;
+        auto vec = [&](double* v, int n) {
+                for (int i = 0; i < n; i++)
+                        if (fscanf(f, "%lf", v + i) != 1) return false;
+                return true;
+        };
+        auto joint = [&](int& j) { return fscanf(f, "%d", &j) == 1 && j >= 0 && j < out->nq; };
+        auto trig = [&](gato_trig* t, int32_t& n, int cap) {
+                int cnt = 0;
+                if (fscanf(f, "%d", &cnt) != 1 || cnt < 0 || cnt > cap) return false;
+                n = cnt;
+                for (int i = 0; i < cnt; i++) {
+                        int idx, k;
+                        double coef;
+                        if (fscanf(f, "%d %lf %d", &idx, &coef, &k) != 3) return false;
+                        t[i] = gato_trig{idx, k, coef};
+                }
+                return true;
+        };
+        while (!ended && fscanf(f, "%63s", key) == 1) {
+                const std::string k = key;
+                int               j = 0;
+                if (k == "end") {
+                        ended = true;
+                } else if (k == "name") {
+                        char nm[64];
+                        if (fscanf(f, "%63s", nm) != 1) return bad("name");
+                        snprintf(out->name, sizeof(out->name), "%.31s", nm);
+                } else if (k == "nq") {
+                        if (fscanf(f, "%d", &out->nq) != 1 || out->nq < 1 || out->nq > GATO_MODEL_MAX_NQ) return bad("nq out of range");
+                } else if (k == "style") {
+                        if (fscanf(f, "%d", &out->style) != 1) return bad("style");
+                } else if (!out->nq) {
+                        return bad("nq must come before the tables");
+                } else if (k == "joint_limit") {
+                        if (!vec(out->joint_limit, out->nq)) return bad(k);
+                } else if (k == "vel_limit") {
+                        if (!vec(out->vel_limit, out->nq)) return bad(k);
+                } else if (k == "ctrl_limit") {
+                        if (!vec(out->ctrl_limit, out->nq)) return bad(k);
+                } else if (k == "X") {
+                        if (!joint(j) || !vec(out->X + 36 * j, 36)) return bad(k);
+                } else if (k == "I") {
+                        if (!joint(j) || !vec(out->I + 36 * j, 36)) return bad(k);
+                } else if (k == "Xhom") {
+                        if (!joint(j) || !vec(out->Xhom + 16 * j, 16)) return bad(k);
+                } else if (k == "dXhom") {
+                        if (!joint(j) || !vec(out->dXhom + 16 * j, 16)) return bad(k);
+                } else if (k == "x_trig") {
+                        if (!trig(out->x_trig, out->n_x_trig, GATO_MODEL_MAX_TRIG * GATO_MODEL_MAX_NQ)) return bad(k);
+                } else if (k == "xh_trig") {
+                        if (!trig(out->xh_trig, out->n_xh_trig, 8 * GATO_MODEL_MAX_NQ)) return bad(k);
+                } else if (k == "dxh_trig") {
+                        if (!trig(out->dxh_trig, out->n_dxh_trig, 8 * GATO_MODEL_MAX_NQ)) return bad(k);
+                } else {
+                        return bad("unknown record '" + k + "'");
+                }
+        }
+        if (!ended) return bad("truncated (no 'end' record)");
+        fclose(f);
+        return GATO_OK;
+}
+
+int gato_model_register(const gato_model* m)
+{
+        if (!m) return GATO_ERR_ARG;
+        RegisteredModel r;
+        r.desc = *m;
+        if (const char* why = rt_model_from_desc(*m, r.rt)) {
+                g_create_error = std::string("gato_model_register: ") + why;
+                return GATO_ERR_UNSUPPORTED;
+        }
+        std::lock_guard<std::mutex> lk(g_model_mu);
+        // registering the same tables again returns the id they already have
+        for (size_t i = 0; i < g_models.size(); i++)
+                if (memcmp(&g_models[i].rt, &r.rt, sizeof(RtModel)) == 0) return GATO_PLANT_MODEL0 + (int)i;
+        if ((int)g_models.size() >= kRtSlots) {
+                g_create_error = "gato_model_register: all model slots are in use";
+                return GATO_ERR_UNSUPPORTED;
+        }
+        g_models.push_back(r);
+        return GATO_PLANT_MODEL0 + (int)g_models.size() - 1;
+}
+
 int gato_create(gato_solver** out, int plant, int N, int B, int device, void* stream, const gato_params* prm)
 {
-        if (!out || !prm || (plant != 0 && plant != 1) || N < 3 || B < 1) {
+        const int nq = plant_nq(plant);
+        if (!out || !prm || !nq || N < 3 || B < 1) {
                 g_create_error = "invalid argument";
                 return GATO_ERR_ARG;
         }
-        gato_solver* s = new gato_solver(plant, N, B, device);
+        gato_solver* s = new gato_solver(plant, nq, N, B, device);
         s->prm = *prm;
         s->max_it = (int)std::max<uint32_t>(prm->max_sqp_iters, 1u);
         s->n_it = (int)prm->max_sqp_iters;
@@ -485,8 +690,22 @@ int gato_create(gato_solver** out, int plant, int N, int B, int device, void* st
                 s->err = "cudaDeviceGetAttribute(multiProcessorCount) failed";
                 return fail(GATO_ERR_CUDA);
         }
-        int rc = plant == GATO_PLANT_IIWA14 ? configure_kernels<Iiwa14>(s) : configure_kernels<Indy7>(s);
+        int rc = with_plant(plant, nq, [&](auto P) { return configure_kernels<decltype(P)>(s); });
         if (rc) return fail(rc);
+        if (plant >= GATO_PLANT_MODEL0) {
+                // the robot's tables -> this device's constant-memory slot of both table-driven kernel groups (idempotent: a slot never changes)
+                RtModel rt;
+                {
+                        std::lock_guard<std::mutex> lk(g_model_mu);
+                        rt = g_models[s->model_slot].rt;
+                }
+                cudaError_t ue = nq == 6 ? upload_rt_model_kkt<RtPlant<6>>(s->model_slot, rt) : upload_rt_model_kkt<RtPlant<7>>(s->model_slot, rt);
+                if (ue == cudaSuccess) ue = nq == 6 ? upload_rt_model_merit<RtPlant<6>>(s->model_slot, rt) : upload_rt_model_merit<RtPlant<7>>(s->model_slot, rt);
+                if (ue != cudaSuccess) {
+                        s->err = std::string("uploading the robot model failed: ") + cudaGetErrorString(ue);
+                        return fail(GATO_ERR_CUDA);
+                }
+        }
         const Dims&  d = s->d;
         const size_t b = B, it = s->max_it;
         cudaError_t  e = cudaSuccess;
@@ -736,10 +955,7 @@ int gato_ee_pos(gato_solver* s, const float* h_q, int n, float* h_ee)
                 CUDA_TRY(s, s->ee_out.alloc((size_t)n * 3));
         }
         CUDA_TRY(s, cudaMemcpyAsync(s->ee_q.p, h_q, sizeof(float) * (size_t)n * nq, cudaMemcpyHostToDevice, s->stream));
-        if (s->plant == GATO_PLANT_IIWA14)
-                enqueue_ee_pos<Iiwa14>(n, s->ee_q.p, s->ee_out.p, s->stream);
-        else
-                enqueue_ee_pos<Indy7>(n, s->ee_q.p, s->ee_out.p, s->stream);
+        with_plant(s->plant, nq, [&](auto P) { enqueue_ee_pos<decltype(P)>(n, s->ee_q.p, s->ee_out.p, s->model_slot, s->stream); });
         s->launches++;
         CUDA_TRY(s, cudaGetLastError());
         CUDA_TRY(s, cudaMemcpyAsync(h_ee, s->ee_out.p, sizeof(float) * (size_t)n * 3, cudaMemcpyDeviceToHost, s->stream));
@@ -751,10 +967,7 @@ int gato_sim_forward(gato_solver* s, float* d_xkp1, const float* d_xk, const flo
 {
         if (!s || !d_xkp1 || !d_xk || !d_uk) return GATO_ERR_ARG;
         if (check_dev(s)) return GATO_ERR_CUDA;
-        if (s->plant == GATO_PLANT_IIWA14)
-                enqueue_sim_forward<Iiwa14>(s->B, d_xkp1, d_xk, d_uk, s->fext.p, dt, s->stream);
-        else
-                enqueue_sim_forward<Indy7>(s->B, d_xkp1, d_xk, d_uk, s->fext.p, dt, s->stream);
+        with_plant(s->plant, s->d.nq, [&](auto P) { enqueue_sim_forward<decltype(P)>(s->B, d_xkp1, d_xk, d_uk, s->fext.p, dt, s->model_slot, s->stream); });
         s->launches++;
         CUDA_TRY(s, cudaGetLastError());
         return GATO_OK;
@@ -976,10 +1189,7 @@ int gato_mpc_local_async(gato_solver* s, const float* d_in, int score, float sim
         if (int rc = dispatch_enqueue(s, s->mpc_xu.p, s->mpc_xs.p, s->mpc_ref.p, timestep)) return rc;
         if (score) {
                 const float* d_xl = d_in + d.nx + 6 * d.N;
-                if (s->plant == GATO_PLANT_IIWA14)
-                        enqueue_sim_forward<Iiwa14>(B, s->mpc_xnext.p, d_xl, d_xl + d.nx, s->fext.p, sim_dt, s->stream);
-                else
-                        enqueue_sim_forward<Indy7>(B, s->mpc_xnext.p, d_xl, d_xl + d.nx, s->fext.p, sim_dt, s->stream);
+                with_plant(s->plant, d.nq, [&](auto P) { enqueue_sim_forward<decltype(P)>(B, s->mpc_xnext.p, d_xl, d_xl + d.nx, s->fext.p, sim_dt, s->model_slot, s->stream); });
                 k_mpc_score<<<1, 256, 0, s->stream>>>(B, d.nx, s->mpc_xnext.p, d_in, s->mpc_err.p, s->mpc_best.p);
                 s->launches += 2;
         } else {
@@ -1084,7 +1294,7 @@ struct StageSolver {
                 return GATO_OK;
         }
 };
-#define PLANT_CALL(plant, fn, ...) ((plant) == GATO_PLANT_IIWA14 ? fn<Iiwa14>(__VA_ARGS__) : fn<Indy7>(__VA_ARGS__))
+#define PLANT_CALL(plant, fn, ...) with_plant((plant), s->d.nq, [&](auto P_) { fn<decltype(P_)>(__VA_ARGS__); })
 }  // namespace
 
 int gato_stage_kkt(int plant, int N, int B, const float* xu, const float* xs, const float* ref, const float* fext, float dt, const float* cost7, float* Q, float* R, float* q, float* r, float* A,
@@ -1154,16 +1364,10 @@ int gato_stage_merit(int plant, int N, int B, const float* xu, const float* dz, 
         ctx.flags = F_MERIT;
         ctx.ls_merit_log = nullptr;
         if (num_alphas == 1) {
-                if (plant == GATO_PLANT_IIWA14)
-                        launch_merit<Iiwa14, 1>(s, ctx);
-                else
-                        launch_merit<Indy7, 1>(s, ctx);
+                with_plant(plant, s->d.nq, [&](auto P) { launch_merit<decltype(P), 1>(s, ctx); });
                 cudaMemcpyAsync(merit, s->merit_cur.p, sizeof(float) * B, cudaMemcpyDeviceToHost, s->stream);
         } else {
-                if (plant == GATO_PLANT_IIWA14)
-                        launch_merit<Iiwa14, kNumAlphas>(s, ctx);
-                else
-                        launch_merit<Indy7, kNumAlphas>(s, ctx);
+                with_plant(plant, s->d.nq, [&](auto P) { launch_merit<decltype(P), kNumAlphas>(s, ctx); });
                 t.down(merit, s->merit);
         }
         return t.finish();
@@ -1179,10 +1383,7 @@ int gato_stage_linesearch(int plant, int N, int B, float* xu, const float* dz, c
         Ctx ctx = make_ctx(s, s->st_xu.p, s->st_xs.p, s->st_ref.p, 0.01f);
         ctx.flags = F_LS;
         ctx.ls_merit_log = nullptr;
-        if (plant == GATO_PLANT_IIWA14)
-                launch_merit<Iiwa14, kNumAlphas>(s, ctx);
-        else
-                launch_merit<Indy7, kNumAlphas>(s, ctx);
+        with_plant(plant, s->d.nq, [&](auto P) { launch_merit<decltype(P), kNumAlphas>(s, ctx); });
         t.down(xu, s->st_xu), t.down(merit_init, s->merit_cur), t.down(step, s->step), t.down(rho, s->rho), t.down(drho, s->drho);
         return t.finish();
 }

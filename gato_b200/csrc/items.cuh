@@ -17,6 +17,18 @@ template<class P>
 struct Items {
         using R = Rbd<P>;
         static constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ;
+        using DynState = typename R::DynState;
+        // The kernels are written once for the compiled plants and the run-time models (items_rt.cuh), whose Items object carries the model
+        // reference: they construct an Items<P> and call members.  The compiled plants carry their constants in the code: nothing to hold.
+        GATO_HD Items() {}
+        static GATO_HD void prologue(const float* xux, const float* fext, DynState& st) { R::dyn_prologue(xux, xux + NQ, xux + NX, fext, st); }
+        static GATO_HD void sim_step(const float* x, const float* u, const float* fext, float dt, float (&qn)[NQ], float (&qdn)[NQ])
+        {
+                float qdd[NQ];
+                R::forward_dynamics(x, x + NQ, u, fext, qdd);
+                R::integrate(x, x + NQ, qdd, dt, qn, qdn);
+        }
+        static GATO_HD void ee_pos(const float* q, float (&ee)[3]) { R::ee_pos(q, ee); }
 
         // ---- tracking cost gradient / Hessian at (x,u) against ref xyz, weight q_cost (see oracle note) ----
         // terminal: the block is Q_{N-1}, q_{N-1} (the reference's computeR = false instantiation).  pos_form_b: the position entries of the
@@ -243,6 +255,15 @@ struct Items {
                                 val = fmaf(dt, d[rd], val);
                         }
                         putA(c * NX + r, val);
+                });
+        }
+        // column `col` (a run-time value, uniform across the warp) of A: dispatch to the specialised column
+        template<class FA>
+        static GATO_HD void linearize_column_any(int col, const DynState& st, const float* qd, float dt, FA&& putA)
+        {
+                sfor<0, NX>([&](auto cc) {
+                        constexpr int cidx = cc;
+                        if (col == cidx) linearize_column<cidx / NQ, cidx % NQ>(st, qd, dt, putA);
                 });
         }
         // B (from M^-1) and the defect c_{k+1}

@@ -6,7 +6,7 @@
 
 #include "bsqp_ctx.cuh"
 #include "pcg_layout.h"
-#include "rbd.cuh"  // plant tags (Iiwa14, Indy7)
+#include "rbd_rt.cuh"  // plant tags (Iiwa14, Indy7, RtPlant<NQ>), RtModel
 
 namespace gato {
 
@@ -38,8 +38,14 @@ template<class P>
 bool enqueue_merit(const Ctx& c, int num_alphas, cudaStream_t st);
 // end-effector position (forward kinematics) of n joint configurations: q[n][nq] -> ee[n][3]
 template<class P>
-void enqueue_ee_pos(int n, const float* q, float* ee, cudaStream_t st);
+void enqueue_ee_pos(int n, const float* q, float* ee, int model_slot, cudaStream_t st);
 template<class P>
-void enqueue_sim_forward(int B, float* xkp1, const float* xk, const float* uk, const float* fext, float dt, cudaStream_t st);
+void enqueue_sim_forward(int B, float* xkp1, const float* xk, const float* uk, const float* fext, float dt, int model_slot, cudaStream_t st);
+// run-time models: copy the tables into constant-memory slot `slot` of the current device, once per kernel group and nq (every translation
+// unit holds its own copy of the slots)
+template<class P>
+cudaError_t upload_rt_model_kkt(int slot, const RtModel& m);
+template<class P>
+cudaError_t upload_rt_model_merit(int slot, const RtModel& m);
 
 }  // namespace gato

@@ -15,4 +15,11 @@ void enqueue_kkt<GATO_TU_PLANT>(const Ctx& c, cudaStream_t st)
         else
                 k_kkt<GATO_TU_PLANT><<<dim3(warps, 3), 32, 0, st>>>(c);
 }
+#ifdef GATO_RT_TU
+template<>
+cudaError_t upload_rt_model_kkt<GATO_TU_PLANT>(int slot, const RtModel& m)
+{
+        return cudaMemcpyToSymbol(g_rt_models, &m, sizeof(RtModel), sizeof(RtModel) * (size_t)slot, cudaMemcpyHostToDevice);
+}
+#endif
 }  // namespace gato

@@ -43,14 +43,21 @@ bool enqueue_merit<GATO_TU_PLANT>(const Ctx& c, int na, cudaStream_t st)
         return false;
 }
 template<>
-void enqueue_ee_pos<GATO_TU_PLANT>(int n, const float* q, float* ee, cudaStream_t st)
+void enqueue_ee_pos<GATO_TU_PLANT>(int n, const float* q, float* ee, int model_slot, cudaStream_t st)
 {
-        k_ee_pos<GATO_TU_PLANT><<<(n + 63) / 64, 64, 0, st>>>(n, q, ee);
+        k_ee_pos<GATO_TU_PLANT><<<(n + 63) / 64, 64, 0, st>>>(n, q, ee, model_slot);
 }
 template<>
-void enqueue_sim_forward<GATO_TU_PLANT>(int B, float* xkp1, const float* xk, const float* uk, const float* fext, float dt, cudaStream_t st)
+void enqueue_sim_forward<GATO_TU_PLANT>(int B, float* xkp1, const float* xk, const float* uk, const float* fext, float dt, int model_slot, cudaStream_t st)
 {
         const int T = 64, G = (B + T - 1) / T;
-        k_sim_forward<GATO_TU_PLANT><<<G, T, 0, st>>>(B, xkp1, xk, uk, fext, dt);
+        k_sim_forward<GATO_TU_PLANT><<<G, T, 0, st>>>(B, xkp1, xk, uk, fext, dt, model_slot);
 }
+#ifdef GATO_RT_TU
+template<>
+cudaError_t upload_rt_model_merit<GATO_TU_PLANT>(int slot, const RtModel& m)
+{
+        return cudaMemcpyToSymbol(g_rt_models, &m, sizeof(RtModel), sizeof(RtModel) * (size_t)slot, cudaMemcpyHostToDevice);
+}
+#endif
 }  // namespace gato

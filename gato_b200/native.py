@@ -40,6 +40,22 @@ class GatoError(RuntimeError):
     pass
 
 
+MODEL_MAX_NQ, MODEL_MAX_TRIG, PLANT_MODEL0 = 7, 16, 2
+
+
+class GatoTrig(C.Structure):
+    _fields_ = [("idx", C.c_int32), ("k", C.c_int32), ("coef", C.c_double)]
+
+
+class GatoModel(C.Structure):
+    """gato_model of include/gato_b200.h: a robot as data tables."""
+
+    _fields_ = [("name", C.c_char * 32), ("nq", C.c_int32), ("style", C.c_int32), ("X", C.c_double * (36 * MODEL_MAX_NQ)), ("I", C.c_double * (36 * MODEL_MAX_NQ)),
+                ("Xhom", C.c_double * (16 * MODEL_MAX_NQ)), ("dXhom", C.c_double * (16 * MODEL_MAX_NQ)), ("joint_limit", C.c_double * MODEL_MAX_NQ), ("vel_limit", C.c_double * MODEL_MAX_NQ),
+                ("ctrl_limit", C.c_double * MODEL_MAX_NQ), ("n_x_trig", C.c_int32), ("n_xh_trig", C.c_int32), ("n_dxh_trig", C.c_int32), ("x_trig", GatoTrig * (MODEL_MAX_TRIG * MODEL_MAX_NQ)),
+                ("xh_trig", GatoTrig * (8 * MODEL_MAX_NQ)), ("dxh_trig", GatoTrig * (8 * MODEL_MAX_NQ))]
+
+
 _LIB = None
 
 
@@ -97,6 +113,10 @@ def load():
         lib.gato_get_kkt_residuals.argtypes = [vp, f32p, f32p]
     if hasattr(lib, "gato_measure_fp32_peak"):  # absent from older builds loaded through GATO_B200_LIB for A/B runs
         lib.gato_measure_fp32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    lib.gato_model_builtin.argtypes = [C.c_int, C.POINTER(GatoModel)]
+    lib.gato_model_load.argtypes = [C.c_char_p, C.POINTER(GatoModel)]
+    lib.gato_model_save.argtypes = [C.POINTER(GatoModel), C.c_char_p]
+    lib.gato_model_register.argtypes = [C.POINTER(GatoModel)]
     lead = [C.c_int, C.c_int, C.c_int]
     lib.gato_stage_kkt.argtypes = lead + [f32p] * 4 + [C.c_float, f32p] + [f32p] * 7
     lib.gato_stage_schur.argtypes = lead + [f32p] * 11
@@ -115,6 +135,63 @@ def measure_fp32_peak(device=0, packed=True):
     if rc != 0:
         raise GatoError(f"gato_measure_fp32_peak failed ({rc})")
     return float(out.value)
+
+
+class Model:
+    """A robot model as data (gato_model): the compiled robots' tables, a file, or tables edited in Python; `register` makes it a plant name
+    that Solver / GatoBackend / gato_b200.bsqp accept like "iiwa14"."""
+
+    def __init__(self, raw=None):
+        self.raw = raw if raw is not None else GatoModel()
+
+    @classmethod
+    def builtin(cls, plant):
+        m = cls()
+        if load().gato_model_builtin(PLANT_ID[plant], C.byref(m.raw)) != 0:
+            raise GatoError(f"no compiled robot '{plant}'")
+        return m
+
+    @classmethod
+    def load(cls, path):
+        m = cls()
+        if load().gato_model_load(str(path).encode(), C.byref(m.raw)) != 0:
+            raise GatoError(f"gato_model_load failed: {load().gato_last_error(None).decode()}")
+        return m
+
+    def save(self, path):
+        if load().gato_model_save(C.byref(self.raw), str(path).encode()) != 0:
+            raise GatoError(f"gato_model_save failed: {load().gato_last_error(None).decode()}")
+
+    @property
+    def nq(self):
+        return int(self.raw.nq)
+
+    @property
+    def name(self):
+        return self.raw.name.decode()
+
+    def array(self, field):
+        """numpy view (shared memory) of one of the double tables: X, I [nq, 36], Xhom, dXhom [nq, 16], joint_limit, vel_limit, ctrl_limit [nq]"""
+        a = np.ctypeslib.as_array(getattr(self.raw, field))
+        per = {"X": 36, "I": 36, "Xhom": 16, "dXhom": 16}.get(field)
+        return a[: per * self.nq].reshape(self.nq, per) if per else a[: self.nq]
+
+    def trig(self, which):
+        """(idx, coef, k) arrays of the x / xh / dxh trig entries"""
+        n = int(getattr(self.raw, f"n_{which}_trig"))
+        t = getattr(self.raw, f"{which}_trig")
+        return (np.array([t[i].idx for i in range(n)], np.int32), np.array([t[i].coef for i in range(n)], np.float64), np.array([t[i].k for i in range(n)], np.int32))
+
+    def register(self, name=None):
+        """-> plant name usable wherever "iiwa14" / "indy7" is (the library assigns the id; the same tables always get the same id)"""
+        pid = load().gato_model_register(C.byref(self.raw))
+        if pid < PLANT_MODEL0:
+            raise GatoError(f"gato_model_register failed ({pid}): {load().gato_last_error(None).decode()}")
+        name = name or self.name or f"model{pid}"
+        if name in PLANT_ID and PLANT_ID[name] != pid:
+            raise GatoError(f"plant name '{name}' is already taken")
+        PLANT_ID[name], NQ[name] = pid, self.nq
+        return name
 
 
 def make_params(p):

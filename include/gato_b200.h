@@ -66,6 +66,37 @@ typedef struct gato_stats {
         const float*   initial_merit;   /* [B] */
 } gato_stats;
 
+/* Run-time robot models: the constants the reference bakes into GRiD-generated source per robot
+ * (init_XImats, gato/dynamics/iiwa14/iiwa14_grid.cuh:1211-2087; the sin/cos assignment patterns of load_update_XImats_helpers :2212-2293 and
+ * load_update_XmatsHom_helpers :2365-2448; the limits of iiwa14_plant.cuh:36-70), as DATA.  A registered model gets a plant id >= GATO_PLANT_MODEL0
+ * that every entry point taking `plant` accepts (gato_create, gato_dims, gato_stage_*); its solves run the table-driven kernels.
+ * Robots covered: fixed-base serial chains of z-axis revolute joints with nq = 6 or 7.
+ *   X[36 j + 6 c + r]      constant part of the 6x6 Pluecker transform of joint j (column-major); top-right 3x3 block zero, bottom-right = top-left
+ *   I[36 j + 6 c + r]      spatial inertia of link j
+ *   Xhom / dXhom[16 j + 4 c + r]   constant parts of the 4x4 homogeneous transform of joint j and of its derivative w.r.t. q_j
+ *   *_trig                 entry idx (into the flattened array above) = (float)(coef * (double)t[k]), t[k < nq] = sin(q_k), t[k >= nq] = cos(q_{k-nq})
+ *   *_limit                symmetric limits +-L; the reference's margin (JOINT_LIMIT_MARGIN = -0.1) is applied by the library
+ *   style                  limit-barrier terms of the cost Hessian: 1 = iiwa14_plant.cuh:399-420 (second derivatives), 0 = indy7_plant.cuh:385-415 */
+#define GATO_MODEL_MAX_NQ 7
+#define GATO_MODEL_MAX_TRIG 16 /* per joint */
+#define GATO_PLANT_MODEL0 2
+typedef struct gato_trig {
+        int32_t idx, k;
+        double  coef;
+} gato_trig;
+typedef struct gato_model {
+        char      name[32];
+        int32_t   nq, style;
+        double    X[36 * GATO_MODEL_MAX_NQ], I[36 * GATO_MODEL_MAX_NQ], Xhom[16 * GATO_MODEL_MAX_NQ], dXhom[16 * GATO_MODEL_MAX_NQ];
+        double    joint_limit[GATO_MODEL_MAX_NQ], vel_limit[GATO_MODEL_MAX_NQ], ctrl_limit[GATO_MODEL_MAX_NQ];
+        int32_t   n_x_trig, n_xh_trig, n_dxh_trig;
+        gato_trig x_trig[GATO_MODEL_MAX_TRIG * GATO_MODEL_MAX_NQ], xh_trig[8 * GATO_MODEL_MAX_NQ], dxh_trig[8 * GATO_MODEL_MAX_NQ];
+} gato_model;
+int gato_model_builtin(int plant /* GATO_PLANT_INDY7 | GATO_PLANT_IIWA14 */, gato_model* out); /* the compiled robots' tables as a model */
+int gato_model_load(const char* path, gato_model* out); /* text file written by gato_model_save */
+int gato_model_save(const gato_model* m, const char* path);
+int gato_model_register(const gato_model* m); /* plant id >= GATO_PLANT_MODEL0, or a negative gato_status (gato_last_error(NULL) says why) */
+
 /* stream: a cudaStream_t (as void*) or NULL for a solver-owned non-blocking stream. */
 int  gato_create(gato_solver** out, int plant, int knot_points, int batch, int device, void* stream, const gato_params* params);
 void gato_destroy(gato_solver* s);

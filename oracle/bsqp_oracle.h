@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-/* plant: 0 = indy7 (nq 6), 1 = iiwa14 (nq 7) */
+/* plant: 0 = indy7 (nq 6), 1 = iiwa14 (nq 7), >= 2 = a robot registered with gato_oracle_register_model */
 typedef struct gato_oracle gato_oracle;
 
 /* params15 = BSQP ctor order (bsqp.cuh:43): dt, max_sqp_iters, kkt_tol, max_pcg_iters, pcg_tol, solve_ratio, mu,
@@ -35,6 +35,9 @@ int  gato_oracle_solve(gato_oracle*, float* xu, const float* xs, const float* re
                        float* ls_step, int cap_iters, float* final_merit, float* initial_merit, double* solve_time_us);
 int  gato_oracle_sim_forward(gato_oracle*, const float* xk, const float* uk, float dt, float* xkp1);
 void gato_oracle_set_threads(int n);
+/* a robot from data tables (see bsqp_oracle.cpp); returns its plant id (>= 2) or -1 */
+int  gato_oracle_register_model(int nq, int style, const double* table, const double* limits, int nxt, const int* xt_idx, const double* xt_coef, const int* xt_k, int nxht,
+                                const int* xht_idx, const double* xht_coef, const int* xht_k, int ndxht, const int* dxht_idx, const double* dxht_coef, const int* dxht_k);
 
 /* stateless per-stage entry points (same buffers/layouts as the reference kernels) */
 int gato_oracle_stage_kkt(int plant, int N, int B, const float* xu, const float* xs, const float* ref, const float* fext, float dt, const float* cost7, float* Q, float* R, float* q, float* r,

@@ -22,6 +22,27 @@ PARAM_ORDER = ["dt", "max_sqp_iters", "kkt_tol", "max_pcg_iters", "pcg_tol", "so
 COST_ORDER = ["q_cost", "qd_cost", "u_cost", "N_cost", "q_lim_cost", "vel_lim_cost", "ctrl_lim_cost"]
 
 
+def register_model(name, model):
+    """Make a robot given as data tables known to the ORACLE under plant name `name`.  `model` is anything with the surface of
+    gato_b200.native.Model: nq, raw.style, array(field), trig(which) -- plain data, no product code runs here."""
+    if name in PLANT_ID:
+        return name
+    lib = C.CDLL(str(HERE / "libbsqp_oracle.so"))
+    f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    lib.gato_oracle_register_model.argtypes = [C.c_int, C.c_int, f64p, f64p] + [C.c_int, i32p, f64p, i32p] * 3
+    nq = int(model.nq)
+    table = np.concatenate([np.asarray(model.array(k), np.float64).reshape(-1) for k in ("X", "I", "Xhom", "dXhom")])
+    limits = np.concatenate([np.asarray(model.array(k), np.float64).reshape(-1) for k in ("joint_limit", "vel_limit", "ctrl_limit")])
+    args = []
+    for which in ("x", "xh", "dxh"):
+        idx, coef, k = model.trig(which)
+        args += [len(idx), np.ascontiguousarray(idx, np.int32), np.ascontiguousarray(coef, np.float64), np.ascontiguousarray(k, np.int32)]
+    pid = lib.gato_oracle_register_model(nq, int(model.raw.style), np.ascontiguousarray(table), np.ascontiguousarray(limits), *args)
+    assert pid >= 2, pid
+    PLANT_ID[name], NQ[name] = pid, nq
+    return name
+
+
 def params15(p):
     return np.array([p[k] for k in PARAM_ORDER], dtype=np.float32)
 
