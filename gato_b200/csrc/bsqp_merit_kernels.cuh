@@ -12,8 +12,11 @@ namespace gato {
 // =====================================================================================================
 // SPLIT (small batches, where a launch lasts as long as one thread's instruction stream): two threads per (alpha, knot) -- one evaluates the
 // forward dynamics and the defect, the other the tracking cost -- combined as fmaf(mu, defect, cost) exactly like the single-thread version.
+#ifndef GATO_RT_MERIT_MIN_BLOCKS
+#define GATO_RT_MERIT_MIN_BLOCKS 2  // table-driven instantiations (their per-thread state lives in local memory: fewer resident threads, more of it in L1)
+#endif
 template<class P, int NA, bool SPLIT = false>
-__global__ void __launch_bounds__(SPLIT ? 512 : (NA == 1 ? 128 : 256), (NA == 1 || SPLIT) ? 1 : GATO_MERIT_MIN_BLOCKS) k_merit_ls(Ctx c)
+__global__ void __launch_bounds__(SPLIT ? 512 : (NA == 1 ? 128 : 256), (NA == 1 || SPLIT) ? 1 : (is_rt_plant<P> ? GATO_RT_MERIT_MIN_BLOCKS : GATO_MERIT_MIN_BLOCKS)) k_merit_ls(Ctx c)
 {
         constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ;
         const bool overlap = NA > 1 && (c.flags & F_OVERLAP) != 0;

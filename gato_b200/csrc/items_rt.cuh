@@ -23,8 +23,15 @@ struct Items<RtPlant<NQ_>> {
         GATO_HD void cost_grad_hess(const float* xu, const float* ref3, const Costs& cs, FQ&& putQ, Fq&& putq, FR&& putR, Fr&& putr, bool terminal = !WITH_R,
                                     bool pos_form_b = !WITH_R) const
         {
-                float ee[3], J[NQ][3], e[3], h[NQ];
-                R::ee_pos_grad(m, xu, ee, J);
+                // one stack object for every dynamically indexed array of this function (see the note on local arrays in rbd_rt.cuh)
+                struct Work {
+                        typename R::EeWork ew;
+                        float              h[NQ], bq[NQ], bv[NQ], bu[NQ], dq[NQ], dv[NQ], du[NQ];
+                } wk;
+                float ee[3], e[3];
+                R::ee_pos_grad(m, xu, ee, wk.ew);
+                float(&J)[NQ][3] = wk.ew.J;
+                float(&h)[NQ] = wk.h;
                 sfor<0, 3>([&](auto rc) { e[rc] = ee[rc] - ref3[rc]; });
                 const float w = cs.q_cost;
                 sfor<0, NQ>([&](auto ic) {
@@ -34,7 +41,9 @@ struct Items<RtPlant<NQ_>> {
                         h[i] = fmaf(J[i][2], e[2], s);
                 });
                 const int style = m.style;
-                float     bq[NQ], bv[NQ], bu[NQ];  // barrier gradients
+                float(&bq)[NQ] = wk.bq;  // barrier gradients
+                float(&bv)[NQ] = wk.bv;
+                float(&bu)[NQ] = wk.bu;
                 GATO_ROLLED
                 for (int i = 0; i < NQ; i++) {
                         bq[i] = rt_joint_barrier_grad(style, xu[i], m.jl[i][0], m.jl[i][1]);
@@ -47,7 +56,9 @@ struct Items<RtPlant<NQ_>> {
                         }
                 }
                 // diagonal barrier terms first (one evaluation per joint), then the blocks
-                float dq[NQ], dv[NQ], du[NQ];
+                float(&dq)[NQ] = wk.dq;
+                float(&dv)[NQ] = wk.dv;
+                float(&du)[NQ] = wk.du;
                 GATO_ROLLED
                 for (int i = 0; i < NQ; i++) {
                         if (style == 1) {
@@ -95,10 +106,11 @@ struct Items<RtPlant<NQ_>> {
         GATO_HD void prologue(const float* xux, const float* fext, DynState& st) const { R::dyn_prologue(m, xux, xux + NQ, xux + NX, fext, st); }
         // column c = k + W*NQ of A
         template<int W, class FA>
-        GATO_HD void column(int k, const DynState& st, const float* qd, float dt, FA&& putA) const
+        GATO_HD void column(int k, DynState& st, const float* qd, float dt, FA&& putA) const
         {
-                float dc[NQ], d[NQ];
-                R::template rnea_grad_col<W>(m, k, st, qd, dc);
+                R::template rnea_grad_col<W>(m, k, st, qd);
+                float(&dc)[NQ] = st.cw.dc;
+                float(&d)[NQ] = st.cw.d;
                 GATO_ROLLED
                 for (int row = 0; row < NQ; row++) {
                         float val = 0.0f;
@@ -121,7 +133,7 @@ struct Items<RtPlant<NQ_>> {
                 }
         }
         template<class FA>
-        GATO_HD void linearize_column_any(int col, const DynState& st, const float* qd, float dt, FA&& putA) const
+        GATO_HD void linearize_column_any(int col, DynState& st, const float* qd, float dt, FA&& putA) const
         {
                 if (col < NQ)
                         column<0>(col, st, qd, dt, putA);
@@ -182,7 +194,7 @@ struct Items<RtPlant<NQ_>> {
         GATO_HD float tracking_cost(const float* xu, const float* ref3, const Costs& cs) const
         {
                 constexpr int TN = NQ + (LAST ? 0 : NU);
-                float         cv[TN + 3], ee[3];
+                float         cv[TN + 3], ee[3];  // cv: the only dynamically indexed array of this function
                 R::ee_pos(m, xu, ee);
                 GATO_ROLLED
                 for (int i = 0; i < NQ; i++) {

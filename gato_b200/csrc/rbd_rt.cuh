@@ -11,6 +11,14 @@
 // +-0 product changes nothing -- the results are bit-identical to the CPU oracle's dense loops and, for the two compiled robots, to
 // rbd.cuh (tests/test_host_math.py, tests/test_gpu_models.py).
 //
+// Local arrays: every dynamically indexed array of a function lives in ONE work struct (FdWork, DynState with its MinvWork / ColWork union,
+// EeWork) -- a single stack object -- and callees get references into it instead of declaring arrays of their own.  This is deliberate: nvcc
+// 12.9's optimiser merges the stack slots of separately declared local arrays by lifetime, and with minv's scratch (F, U, Dinv), its output
+// Minv and update_X's short-lived sin / cos table as individual locals it gave two SIMULTANEOUSLY LIVE arrays -- F and Minv -- the same address
+// (seen in the SASS of k_sim_forward: both addressed off one base register; wrong M^-1 at every optimisation level except -G, while
+// k_merit_ls, which inlines the same functions, was correct).  Members of one struct cannot be merged; tests/test_gpu_models.py checks every
+// table-driven kernel against the oracle bit for bit.
+//
 // T is the lane type: float (one work item per thread) or f2 (TWO work items per thread as the lanes of Blackwell's packed FFMA2 / FADD2:
 // all items run the same instruction stream, so the packed form halves the instructions per item; each lane is rounded like the scalar
 // operation).
@@ -91,20 +99,29 @@ struct RbdRt {
         using V6 = T[NQ][6];
 
         // ---- X_j(q_j)  (load_update_XImats_helpers) ------------------------------------------------------------
-        static GATO_HD void update_X(const RtModel& m, const T* q, Xmat& X)
+        // t[k] = sin(q_k), t[NQ + k] = cos(q_k)
+        static GATO_HD void sincos(const T* q, T (&t)[2 * NQ])
         {
+                GATO_ROLLED
+                for (int k = 0; k < NQ; k++) {
+                        t[k] = L::map(q[k], [](float a) { return g_sin(a); });
+                        t[NQ + k] = L::map(q[k], [](float a) { return g_cos(a); });
+                }
+        }
+        static GATO_HD T trig_entry(const RtTrig& e, const T (&t)[2 * NQ])
+        {
+                const double coef = e.coef;
+                return L::map(t[e.k + (e.use_cos ? NQ : 0)], [&](float tv) { return (float)(coef * (double)tv); });
+        }
+        static GATO_HD void update_X(const RtModel& m, const T* q, T (&t)[2 * NQ], Xmat& X)
+        {
+                sincos(q, t);
                 GATO_ROLLED
                 for (int j = 0; j < NQ; j++) {
                         sfor<0, 18>([&](auto ec) { X[j][ec] = L::set(m.X[j][ec]); });
                         const int n = m.nxt[j];
                         GATO_ROLLED
-                        for (int i = 0; i < n; i++) {
-                                const RtTrig& e = m.xt[j][i];
-                                const T       ang = q[e.k];
-                                const double  coef = e.coef;
-                                const bool    uc = e.use_cos != 0;
-                                X[j][e.loc] = L::map(ang, [&](float a) { return (float)(coef * (double)(uc ? g_cos(a) : g_sin(a))); });
-                        }
+                        for (int i = 0; i < n; i++) X[j][m.xt[j][i].loc] = trig_entry(m.xt[j][i], t);
                 }
         }
         // entry (R, C) of X_j; (R < 3, C >= 3) is the zero block and must not be asked for
@@ -169,39 +186,41 @@ struct RbdRt {
         }
 
         // ---- RNEA  (inverse_dynamics_inner / _vaf with external wrench; oracle: rnea) -----------------------------
-        template<bool WITH_QDD>
-        static GATO_HD void rnea(const RtModel& m, const Xmat& X, const T* qd, const T* qdd, const T* fext, V6& v, V6& a, V6& f)
+        // One forward sweep carries v_{j-1}, a_{j-1} in registers and finishes f_j right away (each value is computed by the same operations as in
+        // the reference's three sweeps); v and a are only stored when the caller needs them (KEEP_VA: the gradient does, forward dynamics does not).
+        template<bool WITH_QDD, bool KEEP_VA>
+        static GATO_HD void rnea(const RtModel& m, const Xmat& X, const T* qd, const T* qdd, const T* fext, V6* v, V6* a, V6& f)
         {
+                T vj[6], aj[6];
                 sfor<0, 6>([&](auto rc) {
                         constexpr int row = rc;
-                        v[0][row] = L::set(0.0f);
-                        a[0][row] = gravity_row<row>(X[0]);
+                        vj[row] = L::set(0.0f);
+                        aj[row] = gravity_row<row>(X[0]);
                 });
-                v[0][2] = L::add(v[0][2], qd[0]);
-                if constexpr (WITH_QDD) a[0][2] = L::add(a[0][2], qdd[0]);
-                GATO_ROLLED
-                for (int j = 1; j < NQ; j++) {
-                        T vj[6], aj[6];
-                        sfor<0, 6>([&](auto rc) {
-                                constexpr int row = rc;
-                                T             vv = xrow<row>(X[j], v[j - 1]);
-                                T             aa = xrow<row>(X[j], a[j - 1]);
-                                if constexpr (row == 2) {
-                                        vv = L::add(vv, qd[j]);
-                                        if constexpr (WITH_QDD) aa = L::add(aa, qdd[j]);
-                                }
-                                vj[row] = vv, aj[row] = aa;
-                        });
-                        aj[0] = L::fma(vj[1], qd[j], aj[0]);
-                        aj[1] = L::fma(L::neg(vj[0]), qd[j], aj[1]);
-                        aj[3] = L::fma(vj[4], qd[j], aj[3]);
-                        aj[4] = L::fma(L::neg(vj[3]), qd[j], aj[4]);
-                        sfor<0, 6>([&](auto rc) { v[j][rc] = vj[rc], a[j][rc] = aj[rc]; });
-                }
+                vj[2] = L::add(vj[2], qd[0]);
+                if constexpr (WITH_QDD) aj[2] = L::add(aj[2], qdd[0]);
                 GATO_ROLLED
                 for (int j = 0; j < NQ; j++) {
-                        T fj[6], Iv[6], t[6], vj[6], aj[6];
-                        sfor<0, 6>([&](auto rc) { vj[rc] = v[j][rc], aj[rc] = a[j][rc]; });
+                        if (j > 0) {
+                                T nv[6], na[6];
+                                sfor<0, 6>([&](auto rc) {
+                                        constexpr int row = rc;
+                                        T             vv = xrow<row>(X[j], vj);
+                                        T             aa = xrow<row>(X[j], aj);
+                                        if constexpr (row == 2) {
+                                                vv = L::add(vv, qd[j]);
+                                                if constexpr (WITH_QDD) aa = L::add(aa, qdd[j]);
+                                        }
+                                        nv[row] = vv, na[row] = aa;
+                                });
+                                na[0] = L::fma(nv[1], qd[j], na[0]);
+                                na[1] = L::fma(L::neg(nv[0]), qd[j], na[1]);
+                                na[3] = L::fma(nv[4], qd[j], na[3]);
+                                na[4] = L::fma(L::neg(nv[3]), qd[j], na[4]);
+                                sfor<0, 6>([&](auto rc) { vj[rc] = nv[rc], aj[rc] = na[rc]; });
+                        }
+                        if constexpr (KEEP_VA) sfor<0, 6>([&](auto rc) { (*v)[j][rc] = vj[rc], (*a)[j][rc] = aj[rc]; });
+                        T fj[6], Iv[6], t[6];
                         sfor<0, 6>([&](auto rc) {
                                 constexpr int row = rc;
                                 fj[row] = irow<row>(m.I[j], aj);
@@ -224,10 +243,16 @@ struct RbdRt {
         }
 
         // ---- direct M^-1  (direct_minv_inner; oracle: minv); Minv[col*NQ+row], upper triangle valid ------------------
-        static GATO_HD void minv(const RtModel& m, const Xmat& X, T (&Minv)[NQ * NQ])
+        // scratch of minv: F[j] = column j of the current level's F
+        struct MinvWork {
+                T F[NQ][6], U[NQ][6], Dinv[NQ];
+        };
+        static GATO_HD void minv(const RtModel& m, const Xmat& X, MinvWork& w, T (&Minv)[NQ * NQ])
         {
-                T IA[36], U[NQ][6], Dinv[NQ];
-                T F[NQ][6];  // column j of the current level's F
+                T IA[36];
+                T(&F)[NQ][6] = w.F;
+                T(&U)[NQ][6] = w.U;
+                T(&Dinv)[NQ] = w.Dinv;
                 sfor<0, NQ * NQ>([&](auto ic) { Minv[ic] = L::set(0.0f); });
                 GATO_ROLLED
                 for (int j = 0; j < NQ; j++) sfor<0, 6>([&](auto rc) { F[j][rc] = L::set(0.0f); });
@@ -303,7 +328,7 @@ struct RbdRt {
         static GATO_HD T minv_sym(const T (&Minv)[NQ * NQ], int row, int col) { return (row <= col) ? Minv[col * NQ + row] : Minv[row * NQ + col]; }
         static GATO_HD void fd_finish(const T (&Minv)[NQ * NQ], const T* u, const V6& f, T (&qdd)[NQ])
         {
-                T tau[NQ];
+                T tau[NQ];  // compile-time indices only: registers
                 sfor<0, NQ>([&](auto cc) { tau[cc] = L::sub(u[cc], f[cc][2]); });
                 GATO_ROLLED
                 for (int row = 0; row < NQ; row++) {
@@ -312,33 +337,49 @@ struct RbdRt {
                         qdd[row] = val;
                 }
         }
+        struct FdWork {
+                T        t[2 * NQ];
+                Xmat     X;
+                T        Minv[NQ * NQ];
+                MinvWork mw;
+                V6       f;
+        };
         // forwardDynamics with wrench (iiwa14_plant.cuh:171-180)
         static GATO_HD void forward_dynamics(const RtModel& m, const T* q, const T* qd, const T* u, const T* fext, T (&qdd)[NQ])
         {
-                Xmat X;
-                update_X(m, q, X);
-                T Minv[NQ * NQ];
-                minv(m, X, Minv);
-                V6 v, a, f;
-                rnea<false>(m, X, qd, nullptr, fext, v, a, f);
-                fd_finish(Minv, u, f, qdd);
+                FdWork w;
+                update_X(m, q, w.t, w.X);
+                minv(m, w.X, w.mw, w.Minv);
+                rnea<false, false>(m, w.X, qd, nullptr, fext, nullptr, nullptr, w.f);
+                T out[NQ];
+                fd_finish(w.Minv, u, w.f, out);
+                sfor<0, NQ>([&](auto ic) { qdd[ic] = out[ic]; });
         }
 
         // forwardDynamicsAndGradient with wrench (iiwa14_plant.cuh:229-268): everything the gradient columns share
+        // scratch of one gradient column (rnea_grad_col and the M^-1 product that follows it)
+        struct ColWork {
+                T df[NQ][6], dc[NQ], d[NQ];
+        };
         struct DynState {
                 Xmat X;
                 T    Minv[NQ * NQ];
                 V6   v, a, f, Iv;
                 T    FxvI[NQ][36];
                 T    qdd[NQ];
+                T    t[2 * NQ];
+                union {  // the prologue's M^-1 scratch is dead when the columns start
+                        MinvWork mw;
+                        ColWork  cw;
+                };
         };
         static GATO_HD void dyn_prologue(const RtModel& m, const T* q, const T* qd, const T* u, const T* fext, DynState& st)
         {
-                update_X(m, q, st.X);
-                minv(m, st.X, st.Minv);
-                rnea<false>(m, st.X, qd, nullptr, fext, st.v, st.a, st.f);
+                update_X(m, q, st.t, st.X);
+                minv(m, st.X, st.mw, st.Minv);
+                rnea<false, false>(m, st.X, qd, nullptr, fext, nullptr, nullptr, st.f);
                 fd_finish(st.Minv, u, st.f, st.qdd);
-                rnea<true>(m, st.X, qd, st.qdd, fext, st.v, st.a, st.f);
+                rnea<true, true>(m, st.X, qd, st.qdd, fext, &st.v, &st.a, st.f);
                 GATO_ROLLED
                 for (int j = 0; j < NQ; j++) {
                         T vj[6];
@@ -354,10 +395,12 @@ struct RbdRt {
                 }
         }
         // ---- RNEA gradient (inverse_dynamics_gradient_inner), column k of d c / d{q | qd} (W = 0 | 1) ---------------------
+        // result in st.cw.dc
         template<int W>
-        static GATO_HD void rnea_grad_col(const RtModel& m, int k, const DynState& st, const T* qd, T (&dc)[NQ])
+        static GATO_HD void rnea_grad_col(const RtModel& m, int k, DynState& st, const T* qd)
         {
-                T df[NQ][6];
+                T(&df)[NQ][6] = st.cw.df;
+                T(&dc)[NQ] = st.cw.dc;
                 T dv[6], da[6];
                 GATO_ROLLED
                 for (int j = 0; j < NQ; j++) sfor<0, 6>([&](auto rc) { df[j][rc] = L::set(0.0f); });
@@ -430,29 +473,23 @@ struct RbdRt {
 
         // ---- end-effector position and positional Jacobian (end_effector_pose(_gradient)_inner; oracle: ee_pos_grad) ----------
         // Xh[j] / dXh[j]: the 4x4 homogeneous transform of joint j and its derivative at q_j
-        static GATO_HD void update_Xhom(const RtModel& m, const T* q, T (&Xh)[NQ][16], T (*dXh)[16])
+        struct EeWork {
+                T t[2 * NQ], Xh[NQ][16], dXh[NQ][16], J[NQ][3];
+        };
+        static GATO_HD void update_Xhom(const RtModel& m, const T* q, T (&t)[2 * NQ], T (&Xh)[NQ][16], T (*dXh)[16])
         {
+                sincos(q, t);
                 GATO_ROLLED
                 for (int j = 0; j < NQ; j++) {
                         sfor<0, 16>([&](auto ec) { Xh[j][ec] = L::set(m.Xh[j][ec]); });
                         const int n = m.nxht[j];
                         GATO_ROLLED
-                        for (int i = 0; i < n; i++) {
-                                const RtTrig& e = m.xht[j][i];
-                                const double  coef = e.coef;
-                                const bool    uc = e.use_cos != 0;
-                                Xh[j][e.loc] = L::map(q[e.k], [&](float a) { return (float)(coef * (double)(uc ? g_cos(a) : g_sin(a))); });
-                        }
+                        for (int i = 0; i < n; i++) Xh[j][m.xht[j][i].loc] = trig_entry(m.xht[j][i], t);
                         if (dXh) {
                                 sfor<0, 16>([&](auto ec) { dXh[j][ec] = L::set(m.dXh[j][ec]); });
                                 const int nd = m.ndxht[j];
                                 GATO_ROLLED
-                                for (int i = 0; i < nd; i++) {
-                                        const RtTrig& e = m.dxht[j][i];
-                                        const double  coef = e.coef;
-                                        const bool    uc = e.use_cos != 0;
-                                        dXh[j][e.loc] = L::map(q[e.k], [&](float a) { return (float)(coef * (double)(uc ? g_cos(a) : g_sin(a))); });
-                                }
+                                for (int i = 0; i < nd; i++) dXh[j][m.dxht[j][i].loc] = trig_entry(m.dxht[j][i], t);
                         }
                 }
         }
@@ -483,19 +520,22 @@ struct RbdRt {
                 }
                 out[0] = p[0], out[1] = p[1], out[2] = p[2];
         }
+        struct EePosWork {
+                T t[2 * NQ], Xh[NQ][16];
+        };
         static GATO_HD void ee_pos(const RtModel& m, const T* q, T (&ee)[3])
         {
-                T Xh[NQ][16];
-                update_Xhom(m, q, Xh, nullptr);
-                ee_chain(Xh, nullptr, -1, ee);
+                EePosWork w;
+                update_Xhom(m, q, w.t, w.Xh, nullptr);
+                ee_chain(w.Xh, nullptr, -1, ee);
         }
-        static GATO_HD void ee_pos_grad(const RtModel& m, const T* q, T (&ee)[3], T (&J)[NQ][3])
+        // position and Jacobian (w.J[d] = d ee / d q_d)
+        static GATO_HD void ee_pos_grad(const RtModel& m, const T* q, T (&ee)[3], EeWork& w)
         {
-                T Xh[NQ][16], dXh[NQ][16];
-                update_Xhom(m, q, Xh, dXh);
-                ee_chain(Xh, dXh, -1, ee);
+                update_Xhom(m, q, w.t, w.Xh, w.dXh);
+                ee_chain(w.Xh, w.dXh, -1, ee);
                 GATO_ROLLED
-                for (int d = 0; d < NQ; d++) ee_chain(Xh, dXh, d, J[d]);
+                for (int d = 0; d < NQ; d++) ee_chain(w.Xh, w.dXh, d, w.J[d]);
         }
 
         // ---- trapezoidal integrator  (integrator.cuh:34-37, 143-184) ---------------------------------------

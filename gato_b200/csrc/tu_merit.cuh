@@ -3,9 +3,12 @@
 #include "bsqp_merit_kernels.cuh"
 namespace gato {
 namespace {
+#ifndef GATO_RT_MERIT_THREADS
+#define GATO_RT_MERIT_THREADS 256
+#endif
 inline int merit_threads(int na, int N)
 {
-        const int cap = na == 1 ? 128 : 256;
+        const int cap = na == 1 ? 128 : (is_rt_plant<GATO_TU_PLANT> ? GATO_RT_MERIT_THREADS : 256);
         int       t = na * N;
         t = (t + 31) / 32 * 32;
         return t > cap ? cap : t;
