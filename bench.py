@@ -358,6 +358,16 @@ def main():
         d_tot = max_over_ranks(float(np.sum(d_ms)))
         extra["default_params_workload"] = {"workload": "iiwa14_N32_B512_sqp1_pcgtol1e-4_cap200 (DEFAULT_SOLVER_PARAMS)", "value": B * world * 10 / (d_tot * 1e-3), "unit": "solves/s",
                                             "ms_per_step": d_tot / 10, "pcg_iters_mean_rank0": float(np.mean(d_st["pcg_iters"])), "pcg_iters_max_rank0": int(np.max(d_st["pcg_iters"]))}
+        # run-time robot model: the iiwa14 tables registered as DATA run the table-driven kernels (gato_model_register) -- same
+        # workload, same bits as the compiled kernels (checked), measured the same way
+        wm = make_config("bench", B=B * world)
+        wm["plant"] = native.Model.load(ROOT / "gato_b200" / "models" / "iiwa14.gmdl").register("iiwa14_as_data")
+        m_ms, _, m_st, m_solver, _ = device_timed(wm, sl, B, 10, 3)
+        m_solver.close()
+        m_tot = max_over_ranks(float(np.sum(m_ms)))
+        extra["table_driven_model"] = {"workload": WORKLOAD + ", robot loaded from gato_b200/models/iiwa14.gmdl at run time", "value": B * world * 10 / (m_tot * 1e-3), "unit": "solves/s",
+                                       "ms_per_step": m_tot / 10, "same_integer_outcomes_as_compiled_kernels": bool(np.array_equal(m_st["pcg_iters"], st["pcg_iters"]) and
+                                                                                                                      np.array_equal(m_st["ls_step_size"], st["ls_step_size"]))}
         if world > 1:
             # strong scaling: the SAME 512 solves split over the ranks
             ws = make_config("bench", B=B)

@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
         if (stopped_before(c, c.it)) return;
         __shared__ float stage[ROWS * KktWarp<P, ROWS>::ST];
         __shared__ int   rowbase[32];
-        const int        kind = blockIdx.y;
+        // (measured: dispatching the two long dynamics kinds before the short cost items is SLOWER, 94.6 vs 73.6 us at B = 512 -- eight dynamics warps
+        // per multiprocessor streaming their code at the same time contend for instruction fetch; the cost warps in between stagger them)
+        const int kind = blockIdx.y;
         KktWarp<P, ROWS> w;
         if (!w.init(c, stage, rowbase, kind == 0)) return;
         if (kind == 0) {
