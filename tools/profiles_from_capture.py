@@ -17,7 +17,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 tag, out = sys.argv[1], sys.argv[2]
 G, P = ROOT / "gpurun_out", ROOT / "profiles"
-KERNELS = {"k_pcg": "k_pcg", "k_schur": "k_schur", "k_kkt": "k_kkt", "k_merit_ls8": "k_merit_ls<8>", "k_merit_ls1": "k_merit_ls<1>", "k_pcg_cluster": "k_pcg_cluster"}
+KERNELS = {"k_pcg": "k_pcg", "k_schur": "k_schur", "k_kkt": "k_kkt", "k_merit_ls8": "k_merit_ls<8>", "k_merit_ls1": "k_merit_ls<1>", "k_pcg_cluster": "k_pcg_cluster",
+           "rt_k_kkt": "k_kkt<RtPlant<7>> (table-driven)", "rt_k_merit_ls8": "k_merit_ls<RtPlant<7>, 8> (table-driven)"}
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__cluster_size",
         "launch__waves_per_multiprocessor", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
@@ -45,6 +46,8 @@ for short, name in KERNELS.items():
                 m[k] = {"value": v, "unit": units[i]}
     scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
     dram = sum(m[k]["value"] * scale.get(m[k]["unit"], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum") if k in m)
+    if short.startswith("rt_"):  # evidence of the run-time model kernels only: bench.py's traffic table is about the compiled kernels
+        pass
     traffic[name] = {"dram_bytes_per_launch": dram, "counters": m, "capture": f"ncu --set full --clock-control none, one launch inside the bench workload (B=512)" if short != "k_pcg_cluster" else "ncu --set full, one launch inside BASELINE config 4 (iiwa14, N=128, B=1024)"}
     sass = G / f"{tag}_{short}_source_sass.csv"
     txt = subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_source_summary.py"), str(sass), "14"], capture_output=True, text=True).stdout
