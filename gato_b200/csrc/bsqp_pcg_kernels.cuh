@@ -792,7 +792,7 @@ __device__ __forceinline__ void cluster_sync()
 template<class P>
 struct ClusterGeom {
         static constexpr int NX = 2 * P::NQ;
-        static constexpr int NB = (P::NQ == 7) ? 32 : 40;  // block rows per CTA: NB * NX is a multiple of 32 (448 = 14 warps, 480 = 15 warps)
+        static constexpr int NB = (P::NQ == 6) ? 40 : 32;  // block rows per CTA: NB * NX is a multiple of 32 (nq 6: 480 = 15 warps, 7: 448 = 14 warps, 8: 512 = 16 warps)
         static constexpr int T = NB * NX;
         static_assert(T % 32 == 0 && T <= 512, "whole warps, one row per thread");
         __host__ __device__ static constexpr int ctas(int N) { return (N + NB - 1) / NB; }

@@ -74,14 +74,15 @@ int plant_nq(int plant)
         const int                   i = plant - GATO_PLANT_MODEL0;
         return (i >= 0 && i < (int)g_models.size()) ? g_models[i].rt.nq : 0;
 }
-// f(plant tag): the compiled plants and the table-driven instantiations for nq = 6 / 7
+// f(plant tag): the compiled plants and the table-driven instantiations for nq = 6 / 7 / 8
 template<class F>
 auto with_plant(int plant, int nq, F&& f)
 {
         if (plant == GATO_PLANT_INDY7) return f(Indy7{});
         if (plant == GATO_PLANT_IIWA14) return f(Iiwa14{});
         if (nq == 6) return f(RtPlant<6>{});
-        return f(RtPlant<7>{});
+        if (nq == 7) return f(RtPlant<7>{});
+        return f(RtPlant<8>{});
 }
 
 }  // namespace
@@ -699,8 +700,15 @@ int gato_create(gato_solver** out, int plant, int N, int B, int device, void* st
                         std::lock_guard<std::mutex> lk(g_model_mu);
                         rt = g_models[s->model_slot].rt;
                 }
-                cudaError_t ue = nq == 6 ? upload_rt_model_kkt<RtPlant<6>>(s->model_slot, rt) : upload_rt_model_kkt<RtPlant<7>>(s->model_slot, rt);
-                if (ue == cudaSuccess) ue = nq == 6 ? upload_rt_model_merit<RtPlant<6>>(s->model_slot, rt) : upload_rt_model_merit<RtPlant<7>>(s->model_slot, rt);
+                const cudaError_t ue = with_plant(plant, nq, [&](auto P) -> cudaError_t {
+                        using Pl = decltype(P);
+                        if constexpr (is_rt_plant<Pl>) {
+                                const cudaError_t e1 = upload_rt_model_kkt<Pl>(s->model_slot, rt);
+                                return e1 != cudaSuccess ? e1 : upload_rt_model_merit<Pl>(s->model_slot, rt);
+                        } else {
+                                return cudaSuccess;
+                        }
+                });
                 if (ue != cudaSuccess) {
                         s->err = std::string("uploading the robot model failed: ") + cudaGetErrorString(ue);
                         return fail(GATO_ERR_CUDA);

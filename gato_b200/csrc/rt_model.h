@@ -2,8 +2,8 @@
 // table-driven dynamics (rbd_rt.cuh) reads from constant memory -- what lets a new robot in from a data file without code generation
 // (the reference bakes these numbers into generated source: iiwa14_grid.cuh:1211-2087, 2212-2293, 2365-2448).
 //
-// Robots covered: fixed-base serial chains of z-axis revolute joints (what GRiD generates for the reference), nq = 6 or 7 (the linear-algebra
-// kernels are instantiated for nx = 12 and 14).  A Pluecker transform X_j(q_j) = [E 0; B E] is held as its 18 independent entries: E = X[0:3,0:3]
+// Robots covered: fixed-base serial chains of z-axis revolute joints (what GRiD generates for the reference), nq = 6, 7 or 8 (the
+// kernels are instantiated for nx = 12, 14 and 16).  A Pluecker transform X_j(q_j) = [E 0; B E] is held as its 18 independent entries: E = X[0:3,0:3]
 // (the bottom-right block is a copy, iiwa14_grid.cuh:2287-2291) and B = X[3:6,0:3]; the top-right block is structurally zero for every joint.
 #pragma once
 #include "../../include/gato_b200.h"
@@ -13,14 +13,15 @@ namespace gato {
 constexpr int kRtMaxQ = GATO_MODEL_MAX_NQ;
 constexpr int kRtMaxXTrig = GATO_MODEL_MAX_TRIG;  // sin/cos-dependent entries of one joint's X (8 for both reference robots)
 constexpr int kRtMaxHTrig = 8;                    // ... of one joint's 4x4 homogeneous transform (4)
-constexpr int kRtSlots = 4;                       // models resident in constant memory at a time (plant ids 2 .. 2 + kRtSlots - 1)
+constexpr int kRtSlots = 8;                       // models resident in constant memory at a time (plant ids 2 .. 2 + kRtSlots - 1); 8 x 7 KB of the 64 KB
 
 // entry `loc` of a joint's matrix = (float)(coef * (double)(use_cos ? cos(q_k) : sin(q_k)))
 struct RtTrig {
         int    loc;  // X: compact index 0..17 (see x_compact); Xhom / dXhom: 4 * col + row
-        int    k, use_cos;
+        short  k, use_cos;
         double coef;
 };
+static_assert(sizeof(RtTrig) == 16, "two trig entries per 32 bytes of constant memory");
 
 struct RtModel {
         int   nq, style;  // style 1: iiwa14-type limit barriers in the cost Hessian (iiwa14_plant.cuh:103-155), 0: indy7-type (indy7_plant.cuh:133-147)
@@ -38,7 +39,7 @@ constexpr int x_compact(int row, int col) { return row < 3 ? 3 * col + row : 9 +
 // gato_model (file content, doubles) -> RtModel; returns 0 or a message describing what the model violates
 inline const char* rt_model_from_desc(const gato_model& d, RtModel& m)
 {
-        if (d.nq != 6 && d.nq != 7) return "nq must be 6 or 7 (the linear-algebra kernels are instantiated for nx = 12 and 14)";
+        if (d.nq < 6 || d.nq > 8) return "nq must be 6, 7 or 8 (the kernels are instantiated for nx = 12, 14 and 16)";
         if (d.style != 0 && d.style != 1) return "style must be 0 (indy7-type barriers) or 1 (iiwa14-type)";
         m = RtModel{};
         m.nq = d.nq, m.style = d.style;
@@ -75,7 +76,7 @@ inline const char* rt_model_from_desc(const gato_model& d, RtModel& m)
                         } else {
                                 t.loc = loc;
                         }
-                        t.k = k % nq, t.use_cos = k >= nq ? 1 : 0, t.coef = src[i].coef;
+                        t.k = (short)(k % nq), t.use_cos = (short)(k >= nq ? 1 : 0), t.coef = src[i].coef;
                 }
                 return nullptr;
         };

@@ -40,7 +40,7 @@ class GatoError(RuntimeError):
     pass
 
 
-MODEL_MAX_NQ, MODEL_MAX_TRIG, PLANT_MODEL0 = 7, 16, 2
+MODEL_MAX_NQ, MODEL_MAX_TRIG, PLANT_MODEL0 = 8, 16, 2
 
 
 class GatoTrig(C.Structure):

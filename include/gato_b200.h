@@ -70,14 +70,14 @@ typedef struct gato_stats {
  * (init_XImats, gato/dynamics/iiwa14/iiwa14_grid.cuh:1211-2087; the sin/cos assignment patterns of load_update_XImats_helpers :2212-2293 and
  * load_update_XmatsHom_helpers :2365-2448; the limits of iiwa14_plant.cuh:36-70), as DATA.  A registered model gets a plant id >= GATO_PLANT_MODEL0
  * that every entry point taking `plant` accepts (gato_create, gato_dims, gato_stage_*); its solves run the table-driven kernels.
- * Robots covered: fixed-base serial chains of z-axis revolute joints with nq = 6 or 7.
+ * Robots covered: fixed-base serial chains of z-axis revolute joints with nq = 6, 7 or 8.
  *   X[36 j + 6 c + r]      constant part of the 6x6 Pluecker transform of joint j (column-major); top-right 3x3 block zero, bottom-right = top-left
  *   I[36 j + 6 c + r]      spatial inertia of link j
  *   Xhom / dXhom[16 j + 4 c + r]   constant parts of the 4x4 homogeneous transform of joint j and of its derivative w.r.t. q_j
  *   *_trig                 entry idx (into the flattened array above) = (float)(coef * (double)t[k]), t[k < nq] = sin(q_k), t[k >= nq] = cos(q_{k-nq})
  *   *_limit                symmetric limits +-L; the reference's margin (JOINT_LIMIT_MARGIN = -0.1) is applied by the library
  *   style                  limit-barrier terms of the cost Hessian: 1 = iiwa14_plant.cuh:399-420 (second derivatives), 0 = indy7_plant.cuh:385-415 */
-#define GATO_MODEL_MAX_NQ 7
+#define GATO_MODEL_MAX_NQ 8
 #define GATO_MODEL_MAX_TRIG 16 /* per joint */
 #define GATO_PLANT_MODEL0 2
 typedef struct gato_trig {

@@ -129,7 +129,9 @@ int hostchk_rt_set_model(const gato_model* m, char* why)
 int hostchk_rt_stage_kkt(int variant, int N, int B, const float* xu, const float* xs, const float* ref, const float* fext, float dt, const float* cost7, float* Q, float* R, float* q, float* r,
                          float* A, float* Bm, float* c)
 {
-        if (g_model.nq == 7)
+        if (g_model.nq == 8)
+                stage_kkt<8>(variant, N, B, xu, xs, ref, fext, dt, cost7, Q, R, q, r, A, Bm, c);
+        else if (g_model.nq == 7)
                 stage_kkt<7>(variant, N, B, xu, xs, ref, fext, dt, cost7, Q, R, q, r, A, Bm, c);
         else
                 stage_kkt<6>(variant, N, B, xu, xs, ref, fext, dt, cost7, Q, R, q, r, A, Bm, c);
@@ -138,7 +140,9 @@ int hostchk_rt_stage_kkt(int variant, int N, int B, const float* xu, const float
 int hostchk_rt_stage_merit(int split, int N, int B, const float* xu, const float* dz, const float* xs, const float* ref, const float* mu, const float* fext, float dt, const float* cost7, int na,
                            float* merit)
 {
-        if (g_model.nq == 7)
+        if (g_model.nq == 8)
+                stage_merit<8>(split, N, B, xu, dz, xs, ref, mu, fext, dt, cost7, na, merit);
+        else if (g_model.nq == 7)
                 stage_merit<7>(split, N, B, xu, dz, xs, ref, mu, fext, dt, cost7, na, merit);
         else
                 stage_merit<6>(split, N, B, xu, dz, xs, ref, mu, fext, dt, cost7, na, merit);
@@ -146,7 +150,9 @@ int hostchk_rt_stage_merit(int split, int N, int B, const float* xu, const float
 }
 int hostchk_rt_dyn(int packed, int n, const float* x, const float* u, const float* fext, float* qdd, float* ee)
 {
-        if (g_model.nq == 7)
+        if (g_model.nq == 8)
+                dyn<8>(packed, n, x, u, fext, qdd, ee);
+        else if (g_model.nq == 7)
                 dyn<7>(packed, n, x, u, fext, qdd, ee);
         else
                 dyn<6>(packed, n, x, u, fext, qdd, ee);

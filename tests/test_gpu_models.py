@@ -90,3 +90,59 @@ def test_headline_shape_with_a_registered_model(oracle_built):
         assert n_mismatch(rc[k], rr[k]) == 0, k
     print(f"device ms: compiled {rc['device_time_ms']:.3f}  table-driven {rr['device_time_ms']:.3f}")
     sc.close(), sr.close()
+
+
+@pytest.mark.parametrize("N,B", [(12, 4), (30, 3), (32, 2), (40, 2)])
+def test_eight_joint_robot_every_stage_and_whole_solves(oracle_built, N, B):
+    """nx = 16: no reference robot has eight joints, so k_schur / k_pcg / k_pcg_stream / k_pcg_cluster are instantiated for this size only for
+    run-time models.  Every stage and whole solves against the oracle, bit for bit (N = 30: register-resident k_pcg at 512 threads; N = 32, 40:
+    (N + 2) nx > 512 -> the cluster kernel with one / two CTAs per solve after k_pcg_stream's K2 phase)."""
+    from gato_b200.native import GatoBackend
+    from gato_b200.workloads import DEFAULT_SOLVER_PARAMS
+    from oracle import pyapi
+    from oracle.pyapi import Backend
+    from test_models_host import eight_joint_robot, random_workload
+
+    model = eight_joint_robot()
+    gplant, oplant = model.register("chain8"), pyapi.register_model("chain8", model)
+    o, g = Backend("oracle", oplant, N), GatoBackend(gplant, N)
+    d = o.d
+    assert d["nx"] == 16
+    w = random_workload(8, N, B, seed=N)
+    rng = np.random.default_rng(3)
+    xu, fext = w["xu"], rng.normal(0, 2, (B, 6)).astype(np.float32)
+    p = dict(DEFAULT_SOLVER_PARAMS, dt=0.01, vel_lim_cost=0.002, ctrl_lim_cost=0.001)
+    rho = np.full(B, p["rho"], np.float32)
+    rho[1::2] = 1e-3
+    mu = np.full(B, 10, np.float32)
+    ko, kg = o.stage_kkt(B, xu, w["xs"], w["ref"], fext, w["dt"], p), g.stage_kkt(B, xu, w["xs"], w["ref"], fext, w["dt"], p)
+    for k in ko:
+        assert n_mismatch(kg[k], ko[k]) == 0, f"kkt {k}"
+    so, sg = o.stage_schur(B, ko, rho), g.stage_schur(B, ko, rho)
+    for k in so:
+        assert n_mismatch(sg[k], so[k]) == 0, f"schur {k}"
+    lam0 = np.zeros((B, d["vecp"]), np.float32)
+    for eps, cap in ((1e-4, 200), (-1.0, 20), (1e-4, 0)):
+        lo, io = o.stage_pcg(B, so["S"], so["Pinv"], so["gamma"], lam0, np.full(B, eps, np.float32), cap)
+        lg, ig = g.stage_pcg(B, so["S"], so["Pinv"], so["gamma"], lam0, np.full(B, eps, np.float32), cap)
+        assert np.array_equal(ig, io) and n_mismatch(lg, lo) == 0, (eps, cap)
+    dzo = o.stage_dz(B, lo, so["Qinv"], so["Rinv"], ko["q"], ko["r"], ko["A"], ko["Bm"])
+    dzg = g.stage_dz(B, lo, so["Qinv"], so["Rinv"], ko["q"], ko["r"], ko["A"], ko["Bm"])
+    for a, b in zip(dzg, dzo):
+        assert n_mismatch(a, b) == 0
+    for na in (1, 8):
+        mo = o.stage_merit(B, xu, dzo[0], w["xs"], w["ref"], mu, fext, w["dt"], p, na)
+        mg = g.stage_merit(B, xu, dzo[0], w["xs"], w["ref"], mu, fext, w["dt"], p, na)
+        assert n_mismatch(mg, mo) == 0, f"merit x{na}"
+    for prm in (dict(p, max_sqp_iters=3), dict(p, max_sqp_iters=4, max_pcg_iters=30, pcg_tol=-1.0)):
+        so_, sg_ = o.solver(B, prm), g.solver(B, prm)
+        so_.set_batch("f_ext", fext), sg_.set_batch("f_ext", fext)
+        xin = xu
+        for rep in range(2):
+            ro, rg = so_.solve(xin, w["xs"], w["ref"], w["dt"]), sg_.solve(xin, w["xs"], w["ref"], w["dt"])
+            for k in ("pcg_iters", "sqp_iters", "kkt_converged"):
+                assert np.array_equal(rg[k], ro[k]), k
+            for k in ("XU", "ls_step_size", "ls_min_merit", "final_merit", "initial_merit"):
+                assert n_mismatch(rg[k], ro[k]) == 0, k
+            xin = ro["XU"]
+        so_.close(), sg_.close()

@@ -36,6 +36,52 @@ def derived_robot(base, name, style, seed):
     return m
 
 
+def eight_joint_robot(name="chain8", seed=21):
+    """An 8-joint robot (no reference robot has eight joints): iiwa14 with one more link, a scaled copy of its sixth, appended at the tip."""
+    base = derived_robot("iiwa14", name, 1, seed)
+    m = native.Model()
+    m.raw.name, m.raw.nq, m.raw.style = name.encode(), 8, 1
+    src = 5  # the link that is copied to the tip
+    for f, per in (("X", 36), ("I", 36), ("Xhom", 16), ("dXhom", 16)):
+        a = np.ctypeslib.as_array(getattr(m.raw, f))
+        b = np.ctypeslib.as_array(getattr(base.raw, f))
+        a[: 7 * per] = b[: 7 * per]
+        a[7 * per : 8 * per] = b[src * per : (src + 1) * per] * (0.8 if f == "I" else 1.0)
+    for f in ("joint_limit", "vel_limit", "ctrl_limit"):
+        a, b = np.ctypeslib.as_array(getattr(m.raw, f)), np.ctypeslib.as_array(getattr(base.raw, f))
+        a[:7], a[7] = b[:7], b[src]
+    for which, per in (("x", 36), ("xh", 16), ("dxh", 16)):
+        old, n = getattr(base.raw, f"{which}_trig"), int(getattr(base.raw, f"n_{which}_trig"))
+        new, cnt = getattr(m.raw, f"{which}_trig"), 0
+        def put(idx, k_joint, is_cos, coef):
+            nonlocal cnt
+            new[cnt].idx, new[cnt].k, new[cnt].coef = idx, k_joint + (8 if is_cos else 0), coef
+            cnt += 1
+        for i in range(n):  # t[k < nq] = sin(q_k), t[k >= nq] = cos(q_{k - nq}): re-encode for nq = 8
+            e = old[i]
+            put(e.idx, e.k % 7, e.k >= 7, e.coef)
+        for i in range(n):
+            e = old[i]
+            if e.idx // per == src:
+                put(e.idx + (7 - src) * per, 7, e.k >= 7, e.coef)
+        setattr(m.raw, f"n_{which}_trig", cnt)
+    return m
+
+
+def random_workload(nq, N, B, seed=0):
+    """inputs of a solve for a robot the synthetic BASELINE workloads do not know (they are tied to the two reference robots)"""
+    rng = np.random.default_rng(seed)
+    nx, nu = 2 * nq, nq
+    xu = np.zeros((B, N, nx + nu), np.float32)
+    xu[..., :nq] = rng.uniform(-0.8, 0.8, (B, 1, nq)) + rng.normal(0, 0.05, (B, N, nq))
+    xu[..., nq:nx] = rng.normal(0, 0.2, (B, N, nq))
+    xu[..., nx:] = rng.normal(0, 2.0, (B, N, nu))
+    xu = xu.reshape(B, -1)[:, : (nx + nu) * N - nu].copy()
+    ref = np.zeros((B, N, 6), np.float32)
+    ref[..., :3] = rng.uniform(-0.4, 0.4, (B, 1, 3)) + rng.normal(0, 0.02, (B, N, 3))
+    return dict(xu=xu, xs=xu[:, :nx].copy(), ref=ref.reshape(B, -1), dt=0.01)
+
+
 @pytest.fixture(scope="module")
 def rtlib(oracle_built):
     d = ROOT / "tests" / "host"
@@ -66,7 +112,7 @@ def test_model_file_round_trip_and_registration_checks(tmp_path):
     assert lib.gato_model_register(C.byref(bad.raw)) == -3 and b"top-right" in lib.gato_last_error(None)
     bad = native.Model.builtin("iiwa14")
     bad.raw.nq = 5
-    assert lib.gato_model_register(C.byref(bad.raw)) == -3 and b"nq must be 6 or 7" in lib.gato_last_error(None)
+    assert lib.gato_model_register(C.byref(bad.raw)) == -3 and b"nq must be 6, 7 or 8" in lib.gato_last_error(None)
     bad = native.Model.builtin("indy7")
     bad.raw.x_trig[0].idx = 36 * 6 + 1
     assert lib.gato_model_register(C.byref(bad.raw)) == -3
@@ -81,13 +127,16 @@ def test_model_file_round_trip_and_registration_checks(tmp_path):
     assert lib.gato_dims(2 + 7, 16, C.byref(nx), C.byref(nu), C.byref(traj)) == -1
 
 
-CASES = [("iiwa14", None, 8, 1), ("indy7", None, 16, 3), ("iiwa14", ("custom7", 0, 11), 32, 2), ("indy7", ("custom6", 1, 12), 8, 3)]
+CASES = [("iiwa14", None, 8, 1), ("indy7", None, 16, 3), ("iiwa14", ("custom7", 0, 11), 32, 2), ("indy7", ("custom6", 1, 12), 8, 3), ("chain8", ("chain8",), 12, None)]
 
 
 @pytest.mark.parametrize("base,derive,N,cfg", CASES)
 def test_table_driven_item_math_bit_exact(rtlib, base, derive, N, cfg):
     if derive is None:
         model, oplant = native.Model.builtin(base), base  # the compiled robot's own tables against the oracle's built-in robot
+    elif base == "chain8":
+        model = eight_joint_robot()
+        oplant = pyapi.register_model("chain8", model)
     else:
         model = derived_robot(base, *derive)
         oplant = pyapi.register_model(derive[0], model)
@@ -107,7 +156,12 @@ def test_table_driven_item_math_bit_exact(rtlib, base, derive, N, cfg):
         rtlib.hostchk_rt_dyn(packed, n, x.ravel(), u.ravel(), fe.ravel(), qdd.ravel(), ee.ravel())
         assert n_mismatch(qdd, o["qdd"]) == 0 and n_mismatch(ee, o["ee"][:, :3]) == 0, packed
     B = 3
-    w = make_config(cfg, B=B, N=N)
+    if cfg is None:
+        from gato_b200.workloads import DEFAULT_SOLVER_PARAMS
+
+        w = dict(random_workload(nq, N, B), params=dict(DEFAULT_SOLVER_PARAMS, dt=0.01))
+    else:
+        w = make_config(cfg, B=B, N=N)
     xu = w["xu"] + rng.normal(0, 0.1, w["xu"].shape).astype(np.float32)
     fext = rng.normal(0, 2, (B, 6)).astype(np.float32)
     p = dict(w["params"], vel_lim_cost=0.003, ctrl_lim_cost=0.002)  # exercise every barrier term
