@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
         constexpr int NQ = P::NQ, NX = 2 * NQ, NU = NQ;
         // staged floats per item: kind 0: Q (its nq x nq block and the lower diagonal; everything else in Q is a structural zero) | q |
         // R (diagonal) | r | c0;  kind 1: half of A | c;  kind 2: half of A | B  -- the largest.  26 KB per warp keeps 8 warps per SM.
-        constexpr int ROWS = NX * NQ + NX * NU;
+        // The table-driven instantiations keep their state in local memory: they run better with twice the warps per multiprocessor and stage
+        // one column (nx rows) at a time -- the cost item then sets the size.
+        constexpr int ROWS = is_rt_plant<P> ? (NQ * NQ + NQ + NX + NU + NU + NX) : (NX * NQ + NX * NU);
         if (stopped_before(c, c.it)) return;
         __shared__ float stage[ROWS * KktWarp<P, ROWS>::ST];
         __shared__ int   rowbase[32];
@@ -137,7 +139,36 @@ __global__ void __launch_bounds__(32, GATO_KKT_MIN_BLOCKS) k_kkt(Ctx c)
         sfor<0, 6>([&](auto ic) { fext[ic] = c.fext[6 * w.b + ic]; });
         constexpr int rA = 0, rX = NX * NQ;  // half of A (NX*NQ contiguous floats), then c (kind 1) or B (kind 2)
         const Items<P> it = make_items<P>(c);
-        if (kind == 1) {
+        if constexpr (is_rt_plant<P>) {
+                typename Items<P>::DynState st;
+                it.prologue(w.xux, fext, st);
+                const int half = kind - 1;
+#pragma unroll 1
+                for (int k = 0; k < NQ; k++) {
+                        const int col = k + half * NQ;
+                        if (half == 0)
+                                it.template column<0>(k, st, w.xux + NQ, c.dt, [&](int e, float v) { w.put(e - col * NX, v); });
+                        else
+                                it.template column<1>(k, st, w.xux + NQ, c.dt, [&](int e, float v) { w.put(e - col * NX, v); });
+                        __syncwarp();
+                        w.template flush<NX>(c.A, 0, NX * NX, col * NX, 0, 2);
+                        __syncwarp();
+                }
+                if (half == 0) {
+                        it.defect(st, w.xux, c.dt, [&](int e, float v) { w.put(e, v); });
+                        __syncwarp();
+                        w.template flush<NX>(c.c, 0, NX, 0, 1, 2);
+                } else {
+#pragma unroll 1
+                        for (int cb = 0; cb < NU; cb++) {
+                                it.b_column(st, cb, c.dt, [&](int e, float v) { w.put(e - cb * NX, v); });
+                                __syncwarp();
+                                w.template flush<NX>(c.Bm, 0, NX * NU, cb * NX, 0, 2);
+                                __syncwarp();
+                        }
+                }
+                return;
+        } else if (kind == 1) {
                 it.template linearize_half_rolled<0>(
                     w.xux, fext, c.dt, [&](int e, float v) { w.put(rA + e, v); }, [&](int, float) {}, [&](int e, float v) { w.put(rX + e, v); });
                 __syncwarp();

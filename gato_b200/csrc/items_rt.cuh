@@ -132,6 +132,28 @@ struct Items<RtPlant<NQ_>> {
                         putA(c * NX + r, val);
                 }
         }
+        // the defect c_{k+1} and one column of B, for callers that stage one column at a time
+        template<class Fc>
+        GATO_HD void defect(const DynState& st, const float* xux, float dt, Fc&& putc) const
+        {
+                float qn[NQ], qdn[NQ];
+                R::integrate(xux, xux + NQ, st.qdd, dt, qn, qdn);
+                sfor<0, NQ>([&](auto ic) {
+                        constexpr int i = ic;
+                        putc(i, xux[NX + NU + i] - qn[i]);
+                        putc(i + NQ, xux[NX + NU + NQ + i] - qdn[i]);
+                });
+        }
+        template<class FB>
+        GATO_HD void b_column(const DynState& st, int c, float dt, FB&& putB) const
+        {
+                const float dt_sq_half = (float)((0.5 * (double)dt) * (double)dt);
+                GATO_ROLLED
+                for (int r = 0; r < NX; r++) {
+                        const float d = R::minv_sym(st.Minv, r < NQ ? r : r - NQ, c);
+                        putB(c * NX + r, (r < NQ) ? (dt_sq_half * d) : (dt * d));
+                }
+        }
         template<class FA>
         GATO_HD void linearize_column_any(int col, DynState& st, const float* qd, float dt, FA&& putA) const
         {
