@@ -343,6 +343,7 @@ struct RbdRt {
                 T        Minv[NQ * NQ];
                 MinvWork mw;
                 V6       f;
+                T        qdd[NQ];
         };
         // forwardDynamics with wrench (iiwa14_plant.cuh:171-180)
         static GATO_HD void forward_dynamics(const RtModel& m, const T* q, const T* qd, const T* u, const T* fext, T (&qdd)[NQ])
@@ -351,9 +352,8 @@ struct RbdRt {
                 update_X(m, q, w.t, w.X);
                 minv(m, w.X, w.mw, w.Minv);
                 rnea<false, false>(m, w.X, qd, nullptr, fext, nullptr, nullptr, w.f);
-                T out[NQ];
-                fd_finish(w.Minv, u, w.f, out);
-                sfor<0, NQ>([&](auto ic) { qdd[ic] = out[ic]; });
+                fd_finish(w.Minv, u, w.f, w.qdd);  // (fd_finish indexes its output dynamically: it stays inside the work struct)
+                sfor<0, NQ>([&](auto ic) { qdd[ic] = w.qdd[ic]; });
         }
 
         // forwardDynamicsAndGradient with wrench (iiwa14_plant.cuh:229-268): everything the gradient columns share
