@@ -146,3 +146,13 @@ def test_eight_joint_robot_every_stage_and_whole_solves(oracle_built, N, B):
                 assert n_mismatch(rg[k], ro[k]) == 0, k
             xin = ro["XU"]
         so_.close(), sg_.close()
+
+
+def test_closed_loop_mpc_step_with_a_registered_model(oracle_built):
+    """The device-side MPC step (gato_mpc_step: prepare, solve, sim_forward scoring, winner adoption) with a robot that exists only as data:
+    the whole comparison of tests/test_gpu_mpc.py -- device step vs host composition vs the oracle, bit for bit -- under the registered plant name."""
+    from test_gpu_mpc import test_device_mpc_step_equals_host_composition_and_oracle as mpc_case
+
+    gplant, oplant = _register("iiwa14", ("custom7", 0, 11))
+    assert gplant == oplant == "custom7"
+    mpc_case("custom7", 8, 16)
